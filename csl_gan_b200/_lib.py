@@ -1,0 +1,149 @@
+"""ctypes binding of libcslgan_b200.so -- the only door from Python into the CUDA kernels.
+
+The binding is deliberately thin: raw `tensor.data_ptr()` integers, sizes, and the current
+CUDA stream handle.  There is no CPU or eager-PyTorch fallback: if the library is missing or
+a call fails, a `CslGanCudaError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcslgan_b200.so")
+CG_MAX_KH = 16
+EPI_SUMSQ, EPI_ACCUM, EPI_STORE = 0, 1, 2
+GROUP_SAMPLE, GROUP_SPLITK = 0, 1
+
+
+class CslGanCudaError(RuntimeError):
+    pass
+
+
+class UnfoldGeom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ("C", "H", "W", "KH", "KW", "sh", "sw", "ph", "pw", "dh", "dw", "Ho", "Wo")]
+
+
+class UnfoldPlan(C.Structure):
+    _fields_ = [("n_rho", C.c_int), ("Hs", C.c_int), ("rows", C.c_int), ("slot_stride", C.c_int),
+                ("tap_row0", C.c_int * CG_MAX_KH), ("tap_coloff", C.c_int * CG_MAX_KH),
+                ("rho", C.c_int * CG_MAX_KH), ("a_min", C.c_int)]
+
+
+class ContractDesc(C.Structure):
+    _fields_ = [
+        ("X", C.c_void_p), ("x_pitch", C.c_longlong), ("x_rows", C.c_int), ("x_cols", C.c_longlong),
+        ("Y", C.c_void_p), ("y_pitch", C.c_longlong), ("y_rows", C.c_int), ("y_cols", C.c_longlong),
+        ("M", C.c_int), ("C", C.c_int), ("KH", C.c_int), ("KW", C.c_int),
+        ("tap_row0", C.c_int * CG_MAX_KH), ("tap_coloff", C.c_int * CG_MAX_KH),
+        ("nkb", C.c_int), ("x_slot_stride", C.c_longlong), ("y_slot_stride", C.c_longlong),
+        ("group_mode", C.c_int), ("n_groups", C.c_int),
+        ("slot_lo", C.c_int), ("slot_hi", C.c_int), ("spg", C.c_int),
+        ("n_seg", C.c_int), ("seg_stride", C.c_int),
+        ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong),
+        ("block_n", C.c_int), ("max_ctas", C.c_int),
+    ]
+
+
+_PROTOS = {
+    "cg_version": (C.c_int, []),
+    "cg_last_error": (C.c_char_p, []),
+    "cg_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "cg_plan_unfold": (C.c_int, [C.POINTER(UnfoldGeom), C.POINTER(UnfoldPlan)]),
+    "cg_stage_rows_t": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_stage_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong,
+                                C.c_int, C.c_void_p, C.c_void_p]),
+    "cg_stage_unfold": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(UnfoldGeom), C.POINTER(UnfoldPlan), C.c_float,
+                                  C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cg_contract": (C.c_int, [C.POINTER(ContractDesc), C.c_void_p]),
+    "cg_outer_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p]),
+    "cg_row_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    "cg_vec_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cg_clip_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    "cg_scale_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p]),
+    "cg_permute_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cg_weighted_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "cg_row_stat": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "cg_noise_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double,
+                                    C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_void_p]),
+    "cg_noise_finalize_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_double, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_void_p]),
+    "cg_row_l2_norm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "cg_row_l2_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "cg_vec_max": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "cg_l2_clip": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib: Optional[C.CDLL] = None
+launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
+_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold"}
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is `python -m csl_gan_b200.build`, done by
+    __graft_entry__.build()).  Fails loudly: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CslGanCudaError(
+            f"{LIB_PATH} is missing: build it with `python -m csl_gan_b200.build` "
+            "(the DP hot path has no CPU / eager fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise CslGanCudaError(f"{name}: {lib.cg_last_error().decode(errors='replace')}")
+    if name not in _NO_LAUNCH:
+        launch_count += 1
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def require_cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise CslGanCudaError(f"{what} must live on a CUDA device (got {t.device}); there is no CPU path")
+    if t.dtype != torch.float32:
+        raise CslGanCudaError(f"{what} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def plan_unfold(C_, H, W, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo):
+    g = UnfoldGeom(C_, H, W, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo)
+    p = UnfoldPlan()
+    call("cg_plan_unfold", C.byref(g), C.byref(p))
+    return g, p
+
+
+def device_info():
+    vals = [C.c_int() for _ in range(4)]
+    call("cg_device_info", *[C.byref(v) for v in vals])
+    return tuple(v.value for v in vals)

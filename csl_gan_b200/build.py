@@ -1,0 +1,57 @@
+"""Build recipe for libcslgan_b200.so (hand-written sm_100a CUDA behind the C ABI).
+
+    python -m csl_gan_b200.build            # nvcc -> csl_gan_b200/libcslgan_b200.so
+
+nvcc cross-compiles without a GPU.  The library is built IN-TREE so it travels to the GPU box
+with the repo snapshot; it is git-ignored (*.so).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "abi.cu")
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("abi.cu", "contract.cuh", "kernels.cuh", "ptx.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "cslgan_b200.h")]
+LIB = os.path.join(HERE, "libcslgan_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libcslgan_b200.so")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libcslgan_b200.so")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

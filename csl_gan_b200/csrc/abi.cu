@@ -1,0 +1,436 @@
+// extern "C" entry points of libcslgan_b200.so (see include/cslgan_b200.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/cslgan_b200.h"
+#include "contract.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CG_CHECK(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define CG_LAUNCH_CHECK()                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevInfo {
+  bool ok = false;
+  int sm = 0, max_thr = 0, major = 0, minor = 0;
+};
+
+int dev_info(DevInfo* out) {
+  static std::mutex mu;
+  static DevInfo cache[64];
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail("device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!cache[dev].ok) {
+    CG_CHECK(cudaDeviceGetAttribute(&cache[dev].sm, cudaDevAttrMultiProcessorCount, dev));
+    CG_CHECK(cudaDeviceGetAttribute(&cache[dev].max_thr, cudaDevAttrMaxThreadsPerMultiProcessor, dev));
+    CG_CHECK(cudaDeviceGetAttribute(&cache[dev].major, cudaDevAttrComputeCapabilityMajor, dev));
+    CG_CHECK(cudaDeviceGetAttribute(&cache[dev].minor, cudaDevAttrComputeCapabilityMinor, dev));
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return 0;
+}
+
+inline cudaStream_t S(cg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid for a grid-stride elementwise kernel: enough blocks to cover `n`, capped at 8 waves of the SMs
+int ew_grid(long long n, int block, int sm) {
+  long long g = (n + block - 1) / block;
+  const long long cap = static_cast<long long>(sm) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CG_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) return fail("cuTensorMapEncodeTiled not available from the driver");
+    cached = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = cached;
+  return 0;
+}
+
+// 2-D fp32 matrix [rows][cols] with row pitch `pitch` floats; box = 32 cols x box_rows, SWIZZLE_128B.
+int make_tmap(CUtensorMap* tm, const float* base, long long rows, long long cols, long long pitch, int box_rows) {
+  EncodeTiledFn enc;
+  if (get_encode(&enc)) return 1;
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail("operand base pointer must be 16-byte aligned");
+  if ((pitch * 4) % 16) return fail("operand pitch (%lld floats) must be a multiple of 4", pitch);
+  if (cols > pitch) return fail("operand cols (%lld) exceed pitch (%lld)", cols, pitch);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(cg::kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld pitch=%lld box_rows=%d)",
+                                     static_cast<int>(r), rows, cols, pitch, box_rows);
+  return 0;
+}
+
+int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+
+extern "C" {
+
+int cg_version(void) { return 100; }
+
+const char* cg_last_error(void) { return g_err; }
+
+int cg_device_info(int* sm_count, int* max_threads_per_sm, int* cc_major, int* cc_minor) {
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  if (sm_count) *sm_count = d.sm;
+  if (max_threads_per_sm) *max_threads_per_sm = d.max_thr;
+  if (cc_major) *cc_major = d.major;
+  if (cc_minor) *cc_minor = d.minor;
+  return 0;
+}
+
+int cg_plan_unfold(const cg_unfold_geom* g, cg_unfold_plan* plan) {
+  if (!g || !plan) return fail("null argument");
+  if (g->KH < 1 || g->KH > CG_MAX_KH || g->KW < 1) return fail("unsupported filter size %dx%d", g->KH, g->KW);
+  if (g->sh < 1 || g->sw < 1 || g->dh < 1 || g->dw < 1) return fail("stride/dilation must be >= 1");
+  memset(plan, 0, sizeof(*plan));
+  int a[CG_MAX_KH], rho_of[CG_MAX_KH];
+  int a_min = 1 << 30, a_max = -(1 << 30);
+  int n_rho = 0;
+  for (int kh = 0; kh < g->KH; ++kh) {
+    const int r = kh * g->dh - g->ph;
+    a[kh] = floor_div(r, g->sh);
+    rho_of[kh] = r - a[kh] * g->sh;
+    if (a[kh] < a_min) a_min = a[kh];
+    if (a[kh] > a_max) a_max = a[kh];
+    int j = -1;
+    for (int t = 0; t < n_rho; ++t)
+      if (plan->rho[t] == rho_of[kh]) j = t;
+    if (j < 0) {
+      j = n_rho;
+      plan->rho[n_rho++] = rho_of[kh];
+    }
+    plan->tap_row0[kh] = j * g->KW * g->C;
+  }
+  plan->n_rho = n_rho;
+  plan->a_min = a_min;
+  plan->Hs = g->Ho + a_max - a_min;
+  plan->rows = n_rho * g->KW * g->C;
+  plan->slot_stride = plan->Hs * g->Wo;
+  for (int kh = 0; kh < g->KH; ++kh) plan->tap_coloff[kh] = (a[kh] - a_min) * g->Wo;
+  return 0;
+}
+
+int cg_stage_rows_t(const float* src, int B, int R, float scale, float* dst, long long dst_pitch, int slot0,
+                    float* copy_out, float* sumsq, cg_stream_t stream) {
+  if (B <= 0 || R <= 0) return 0;
+  if (sumsq) CG_CHECK(cudaMemsetAsync(sumsq + slot0, 0, sizeof(float) * B, S(stream)));
+  dim3 grid((R + 31) / 32, (B + 31) / 32), block(32, 8);
+  cg::stage_rows_t_kernel<<<grid, block, 0, S(stream)>>>(src, B, R, scale, dst, dst_pitch, slot0, copy_out, sumsq);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_stage_rows(const float* src, int B, int R, int Q, int Qpad, float scale, float* dst, long long dst_pitch,
+                  int slot0, float* rowsum, cg_stream_t stream) {
+  if (B <= 0 || R <= 0) return 0;
+  if (Qpad < Q) return fail("Qpad (%d) < Q (%d)", Qpad, Q);
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const long long nrows = static_cast<long long>(B) * R;
+  const int block = 256;
+  long long g = (nrows + 7) / 8;
+  if (g > static_cast<long long>(d.sm) * 16) g = static_cast<long long>(d.sm) * 16;
+  cg::stage_rows_kernel<<<static_cast<int>(g), block, 0, S(stream)>>>(src, B, R, Q, Qpad, scale, dst, dst_pitch, slot0,
+                                                                      rowsum);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_unfold_plan* plan, float scale,
+                    float* dst, long long dst_pitch, int slot0, cg_stream_t stream) {
+  if (!g || !plan) return fail("null argument");
+  if (B <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::UnfoldParams p;
+  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W; p.KW = g->KW;
+  p.sh = g->sh; p.sw = g->sw; p.pw = g->pw; p.dw = g->dw;
+  p.Wo = g->Wo; p.Hs = plan->Hs; p.n_rho = plan->n_rho; p.a_min = plan->a_min;
+  for (int j = 0; j < CG_MAX_KH; ++j) p.rho[j] = plan->rho[j];
+  p.scale = scale; p.dst_pitch = dst_pitch; p.slot0 = slot0;
+  const long long total = static_cast<long long>(plan->rows) * B * plan->slot_stride;
+  cg::stage_unfold_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(src, p, dst);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
+  if (!d) return fail("null descriptor");
+  DevInfo dv;
+  if (dev_info(&dv)) return 1;
+  if (dv.major != 10) return fail("cg_contract needs an sm_100-class device (found sm_%d%d)", dv.major, dv.minor);
+  if (d->KH < 1 || d->KH > CG_MAX_KH) return fail("KH out of range");
+  if (d->n_groups <= 0 || d->nkb <= 0) return 0;
+  cg::ContractParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M;
+  p.n_mtiles = (d->M + cg::kBM - 1) / cg::kBM;
+  p.KWC = d->KW * d->C;
+  int bn = d->block_n;
+  if (bn <= 0) {
+    bn = cg::kMaxBN;
+    if (p.KWC < bn) bn = ((p.KWC + 15) / 16) * 16;
+  }
+  if (bn % 16 || bn < 16 || bn > cg::kMaxBN) return fail("block_n must be a multiple of 16 in [16,128]");
+  p.BN = bn;
+  p.n_rb = (p.KWC + bn - 1) / bn;
+  p.C = d->C; p.KH = d->KH; p.KW = d->KW;
+  for (int i = 0; i < CG_MAX_KH; ++i) { p.tap_row0[i] = d->tap_row0[i]; p.tap_coloff[i] = d->tap_coloff[i]; }
+  p.nkb = d->nkb;
+  p.x_slot_stride = d->x_slot_stride; p.y_slot_stride = d->y_slot_stride;
+  p.group_mode = d->group_mode; p.n_groups = d->n_groups;
+  p.slot_lo = d->slot_lo; p.slot_hi = d->slot_hi; p.spg = d->spg;
+  p.n_seg = d->n_seg; p.seg_stride = d->seg_stride;
+  p.epi = d->epi; p.out = d->out; p.out_group_stride = d->out_group_stride;
+  if (p.group_mode == CG_GROUP_SPLITK) {
+    if (p.spg <= 0) return fail("spg must be positive for split-K groups");
+    if (static_cast<long long>(p.n_groups - 1) * p.spg >= (p.slot_hi - p.slot_lo)) return fail("empty split-K group");
+  } else if (p.n_seg <= 0) {
+    return fail("n_seg must be positive");
+  }
+  p.n_items = static_cast<long long>(p.n_groups) * p.KH * p.n_rb * p.n_mtiles;
+
+  CUtensorMap tx, ty;
+  if (make_tmap(&tx, d->X, d->x_rows, d->x_cols, d->x_pitch, cg::kBM)) return 1;
+  if (make_tmap(&ty, d->Y, d->y_rows, d->y_cols, d->y_pitch, bn)) return 1;
+
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kSmemBytes));
+    attr_set[dev] = true;
+  }
+  long long grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
+  if (grid > p.n_items) grid = p.n_items;
+  cg::contract_kernel<<<static_cast<int>(grid), cg::kThreads, cg::kSmemBytes, S(stream)>>>(tx, ty, p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_outer_rows(const float* X, long long x_pitch, const float* Y, long long y_pitch, int M, int P, int slot0,
+                  int B, float* out, cg_stream_t stream) {
+  const long long total = static_cast<long long>(B) * M * P;
+  if (total <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::outer_rows_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(X, x_pitch, Y, y_pitch, M, P, slot0, B, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_row_sumsq(const float* src, long long rows, long long cols, long long ld, float* out, int accumulate,
+                 cg_stream_t stream) {
+  if (rows <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  if (cols <= 256) {
+    long long g = (rows + 7) / 8;
+    if (g > static_cast<long long>(d.sm) * 16) g = static_cast<long long>(d.sm) * 16;
+    cg::row_sumsq_warp_kernel<<<static_cast<int>(g), 256, 0, S(stream)>>>(src, rows, cols, ld, out, accumulate, 0);
+  } else {
+    long long g = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
+    cg::row_sumsq_kernel<<<static_cast<int>(g), 256, 0, S(stream)>>>(src, rows, cols, ld, out, accumulate, 0);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_vec_mul(const float* a, const float* b, float* out, long long n, cg_stream_t stream) {
+  if (n <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::vec_mul_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(a, b, out, n);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C, int clip_lo,
+                    int clip_hi, float* factors, float* norms_out, cg_stream_t stream) {
+  if (n_slots <= 0 || n_params <= 0) return 0;
+  cg::clip_factors_kernel<<<(n_slots + 127) / 128, 128, 0, S(stream)>>>(norm2, n_params, n_slots, per_layer, C, clip_lo,
+                                                                       clip_hi, factors, norms_out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_scale_slots(const float* src, float* dst, int rows, long long pitch, long long slot_stride, int slot_lo,
+                   int slot_hi, const float* factor, cg_stream_t stream) {
+  if (rows <= 0 || slot_hi <= slot_lo) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const long long total = static_cast<long long>(rows) * (slot_hi - slot_lo) * slot_stride;
+  cg::scale_slots_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(src, dst, rows, pitch, slot_stride, slot_lo,
+                                                                          slot_hi, factor);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_permute_accum(const float* T, float* out, int M, int C, int KH, int KW, int accumulate, cg_stream_t stream) {
+  const long long total = static_cast<long long>(M) * C * KH * KW;
+  if (total <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::permute_accum_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(T, out, M, C, KH, KW, accumulate);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_weighted_colsum(const float* rows_in, const float* factor, int slot_lo, int slot_hi, int R, float* out,
+                       int accumulate, cg_stream_t stream) {
+  if (R <= 0) return 0;
+  if (!accumulate) CG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * R, S(stream)));
+  if (slot_hi <= slot_lo) return 0;
+  int ny = (slot_hi - slot_lo + 63) / 64;
+  if (ny > 64) ny = 64;
+  dim3 grid((R + 127) / 128, ny);
+  cg::weighted_colsum_kernel<<<grid, 128, 0, S(stream)>>>(rows_in, factor, slot_lo, slot_hi, R, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int slot_hi, int stat, float scalar,
+                float* out, cg_stream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (slot_hi <= slot_lo) return fail("empty slot range");
+  cg::row_stat_kernel<<<n_rows, 256, 0, S(stream)>>>(norms, n_rows, n_slots, slot_lo, slot_hi, stat, scalar, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int noise_impl(const float* in, float* grad, long long n, double in_div, double std, const float* std_dev,
+                      double noise_div, unsigned long long seed, unsigned long long offset,
+                      unsigned long long* offset_inc, cg_stream_t stream) {
+  if (offset_inc) *offset_inc = 0;
+  if (n <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  if (!std_dev && !(std > 0.0)) {
+    // upstream _generate_noise returns zeros when sigma*C == 0 and draws nothing from the generator
+    if (in) {
+      cg::scale_copy_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(in, grad, n, static_cast<float>(in_div));
+      CG_LAUNCH_CHECK();
+    } else {
+      CG_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n, S(stream)));
+    }
+    return 0;
+  }
+  if (offset % 4) return fail("philox offset must be a multiple of 4");
+  const unsigned int block = 256;
+  unsigned long long grid = (static_cast<unsigned long long>(n) + block - 1) / block;
+  const unsigned long long cap = static_cast<unsigned long long>(d.sm) * (d.max_thr / block);
+  if (grid > cap) grid = cap;
+  if (offset_inc) *offset_inc = ((static_cast<unsigned long long>(n) - 1) / (block * grid * 4) + 1) * 4;
+  cg::noise_finalize_kernel<<<static_cast<unsigned int>(grid), block, 0, S(stream)>>>(
+      in, grad, n, static_cast<float>(in_div), static_cast<float>(std), static_cast<float>(noise_div), seed, offset,
+      std_dev);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, double std, double noise_div,
+                      unsigned long long seed, unsigned long long offset, unsigned long long* offset_inc,
+                      cg_stream_t stream) {
+  return noise_impl(in, grad, n, in_div, std, nullptr, noise_div, seed, offset, offset_inc, stream);
+}
+
+int cg_noise_finalize_dev(const float* in, float* grad, long long n, double in_div, double std_mult,
+                          const float* std_dev, double noise_div, unsigned long long seed, unsigned long long offset,
+                          unsigned long long* offset_inc, cg_stream_t stream) {
+  if (!std_dev) return fail("std_dev must not be null");
+  return noise_impl(in, grad, n, in_div, std_mult, std_dev, noise_div, seed, offset, offset_inc, stream);
+}
+
+int cg_row_l2_norm(const float* src, long long rows, long long cols, float* norms, cg_stream_t stream) {
+  if (rows <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  if (cols <= 256) {
+    long long g = (rows + 7) / 8;
+    if (g > static_cast<long long>(d.sm) * 16) g = static_cast<long long>(d.sm) * 16;
+    cg::row_sumsq_warp_kernel<<<static_cast<int>(g), 256, 0, S(stream)>>>(src, rows, cols, cols, norms, 0, 1);
+  } else {
+    long long g = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
+    cg::row_sumsq_kernel<<<static_cast<int>(g), 256, 0, S(stream)>>>(src, rows, cols, cols, norms, 0, 1);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_row_l2_norm_bwd(const float* g, const float* norms, const float* gout, long long rows, long long cols,
+                       float* gin, cg_stream_t stream) {
+  if (rows <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  long long grid = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
+  cg::row_l2_norm_bwd_kernel<<<static_cast<int>(grid), 256, 0, S(stream)>>>(g, norms, gout, rows, cols, gin);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_vec_max(const float* v, long long n, float* out, cg_stream_t stream) {
+  if (n <= 0) return fail("cg_vec_max on an empty vector");
+  cg::vec_max_kernel<<<1, 1024, 0, S(stream)>>>(v, n, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_l2_clip(const float* t, long long rows, long long cols, float C, float* out, float* norms_out,
+               cg_stream_t stream) {
+  if (rows <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  long long grid = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
+  cg::l2_clip_kernel<<<static_cast<int>(grid), 256, 0, S(stream)>>>(t, rows, cols, C, out, norms_out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

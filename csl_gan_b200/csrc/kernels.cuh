@@ -1,0 +1,402 @@
+// Bandwidth kernels around the contraction: staging (capture), norms, clip factors, permutes,
+// Philox noise, per-sample row norms and L2 clipping.  All coalesced / vectorised where the
+// layout allows, warp-shuffle reductions, grid sized in multiples of the SM count.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+
+#include "../../include/cslgan_b200.h"
+#include "ptx.cuh"
+
+namespace cg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024). Result valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage_rows_t: src[B][R] -> dst[r][slot0+n] (32x32 shared-memory transpose tiles)
+// grid (ceil(R/32), ceil(B/32)), block (32, 8)
+// ------------------------------------------------------------------------------------------
+__global__ void stage_rows_t_kernel(const float* __restrict__ src, int B, int R, float scale,
+                                    float* __restrict__ dst, long long dst_pitch, int slot0,
+                                    float* __restrict__ copy_out, float* __restrict__ sumsq) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int n = n0 + ty + i, r = r0 + tx;
+    float v = 0.f;
+    if (n < B && r < R) {
+      v = scale * src[static_cast<long long>(n) * R + r];
+      if (copy_out) copy_out[static_cast<long long>(slot0 + n) * R + r] = v;
+    }
+    tile[ty + i][tx] = v;
+    if (sumsq) {
+      float s = warp_sum(v * v);
+      if (tx == 0 && n < B) atomicAdd(sumsq + slot0 + n, s);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, n = n0 + tx;
+    if (r < R && n < B) dst[static_cast<long long>(r) * dst_pitch + slot0 + n] = round_tf32(tile[tx][ty + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage_rows: src[B][R][Q] -> dst[r][(slot0+n)*Qpad + q], zero padded; one warp per (n, r) row
+// ------------------------------------------------------------------------------------------
+__global__ void stage_rows_kernel(const float* __restrict__ src, int B, int R, int Q, int Qpad, float scale,
+                                  float* __restrict__ dst, long long dst_pitch, int slot0,
+                                  float* __restrict__ rowsum) {
+  const long long nrows = static_cast<long long>(B) * R;
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < nrows; w += warps_total) {
+    const int n = static_cast<int>(w / R), r = static_cast<int>(w % R);
+    const float* s = src + w * Q;
+    float* d = dst + static_cast<long long>(r) * dst_pitch + static_cast<long long>(slot0 + n) * Qpad;
+    float acc = 0.f;
+    for (int q = lane; q < Qpad; q += 32) {
+      float v = 0.f;
+      if (q < Q) {
+        v = scale * s[q];
+        acc += v;
+      }
+      d[q] = round_tf32(v);
+    }
+    if (rowsum) {
+      acc = warp_sum(acc);
+      if (lane == 0) rowsum[static_cast<long long>(slot0 + n) * R + r] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage_unfold: src[B][C][H][W] -> kw-plane matrix
+//   dst[((j*KW + kw)*C + c)][ (slot0+n)*Hs*Wo + hs*Wo + ow ] = src[n][c][sh*(hs+a_min)+rho_j][ow*sw - pw + kw*dw]
+// One thread per destination element; ow fastest so writes are coalesced and the strided reads
+// of neighbouring kw planes hit the same lines in L1/L2.
+// ------------------------------------------------------------------------------------------
+struct UnfoldParams {
+  int B, C, H, W, KW, sh, sw, pw, dw, Wo, Hs, n_rho, a_min;
+  int rho[CG_MAX_KH];
+  float scale;
+  long long dst_pitch;
+  int slot0;
+};
+
+__global__ void stage_unfold_kernel(const float* __restrict__ src, const __grid_constant__ UnfoldParams p,
+                                    float* __restrict__ dst) {
+  const long long per_row = static_cast<long long>(p.B) * p.Hs * p.Wo;
+  const long long total = static_cast<long long>(p.n_rho) * p.KW * p.C * per_row;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ow = static_cast<int>(i % p.Wo);
+    long long t = i / p.Wo;
+    const int hs = static_cast<int>(t % p.Hs);
+    t /= p.Hs;
+    const int n = static_cast<int>(t % p.B);
+    t /= p.B;
+    const int c = static_cast<int>(t % p.C);
+    t /= p.C;
+    const int kw = static_cast<int>(t % p.KW);
+    const int j = static_cast<int>(t / p.KW);
+    const int h = p.sh * (hs + p.a_min) + p.rho[j];
+    const int w = ow * p.sw - p.pw + kw * p.dw;
+    float v = 0.f;
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W)
+      v = p.scale * src[((static_cast<long long>(n) * p.C + c) * p.H + h) * p.W + w];
+    const long long row = (static_cast<long long>(j) * p.KW + kw) * p.C + c;
+    dst[row * p.dst_pitch + (static_cast<long long>(p.slot0 + n) * p.Hs + hs) * p.Wo + ow] = round_tf32(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// row reductions
+// ------------------------------------------------------------------------------------------
+// one block per row (grid-stride over rows); float4 path when the row is 16-byte aligned
+__device__ __forceinline__ float row_sumsq_device(const float* __restrict__ row, long long cols) {
+  float acc = 0.f;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const long long n4 = cols >> 2;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldg(r4 + i);
+      acc = fmaf(v.x, v.x, acc);
+      acc = fmaf(v.y, v.y, acc);
+      acc = fmaf(v.z, v.z, acc);
+      acc = fmaf(v.w, v.w, acc);
+    }
+    for (long long i = (n4 << 2) + threadIdx.x; i < cols; i += blockDim.x) acc = fmaf(row[i], row[i], acc);
+  } else {
+    for (long long i = threadIdx.x; i < cols; i += blockDim.x) acc = fmaf(row[i], row[i], acc);
+  }
+  return acc;
+}
+
+__global__ void row_sumsq_kernel(const float* __restrict__ src, long long rows, long long cols, long long ld,
+                                 float* __restrict__ out, int accumulate, int take_sqrt) {
+  __shared__ float sh[32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float s = block_sum(row_sumsq_device(src + r * ld, cols), sh);
+    if (threadIdx.x == 0) {
+      if (take_sqrt) s = sqrtf(s);
+      out[r] = accumulate ? out[r] + s : s;
+    }
+  }
+}
+
+// small rows: one warp per row
+__global__ void row_sumsq_warp_kernel(const float* __restrict__ src, long long rows, long long cols, long long ld,
+                                      float* __restrict__ out, int accumulate, int take_sqrt) {
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
+    const float* row = src + r * ld;
+    float acc = 0.f;
+    for (long long i = lane; i < cols; i += 32) acc = fmaf(row[i], row[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (take_sqrt) acc = sqrtf(acc);
+      out[r] = accumulate ? out[r] + acc : acc;
+    }
+  }
+}
+
+// out[n][m][p] = X[m][slot0+n] * Y[p][slot0+n]; p fastest (coalesced writes)
+__global__ void outer_rows_kernel(const float* __restrict__ X, long long x_pitch, const float* __restrict__ Y,
+                                  long long y_pitch, int M, int P, int slot0, int B, float* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * M * P;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int pp = static_cast<int>(i % P);
+    const long long t = i / P;
+    const int m = static_cast<int>(t % M);
+    const int n = static_cast<int>(t / M);
+    out[i] = X[static_cast<long long>(m) * x_pitch + slot0 + n] * Y[static_cast<long long>(pp) * y_pitch + slot0 + n];
+  }
+}
+
+__global__ void vec_mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                               long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = a[i] * b[i];
+}
+
+__global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_params, int n_slots, int per_layer,
+                                    const float* __restrict__ C, int clip_lo, int clip_hi,
+                                    float* __restrict__ factors, float* __restrict__ norms_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const bool clipped = (s >= clip_lo && s < clip_hi);
+  if (per_layer) {
+    for (int k = 0; k < n_params; ++k) {
+      const float n = sqrtf(norm2[static_cast<long long>(k) * n_slots + s]);
+      if (norms_out) norms_out[static_cast<long long>(k) * n_slots + s] = n;
+      const float f = fminf(C[k] / (n + 1e-6f), 1.0f);
+      factors[static_cast<long long>(k) * n_slots + s] = clipped ? f : 1.0f;
+    }
+  } else {
+    float tot = 0.f;
+    for (int k = 0; k < n_params; ++k) tot += norm2[static_cast<long long>(k) * n_slots + s];
+    const float n = sqrtf(tot);
+    if (norms_out) norms_out[s] = n;
+    const float f = fminf(C[0] / (n + 1e-6f), 1.0f);
+    factors[s] = clipped ? f : 1.0f;
+  }
+}
+
+// dst[r][slot*stride + q] = tf32(src * factor[slot]); float4 when everything is 4-aligned
+__global__ void scale_slots_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows,
+                                   long long pitch, long long slot_stride, int slot_lo, int slot_hi,
+                                   const float* __restrict__ factor) {
+  const long long cols = static_cast<long long>(slot_hi - slot_lo) * slot_stride;
+  const long long col0 = static_cast<long long>(slot_lo) * slot_stride;
+  const long long total = static_cast<long long>(rows) * cols;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / cols, cidx = i - r * cols;
+    const int slot = slot_lo + static_cast<int>(cidx / slot_stride);
+    const long long off = r * pitch + col0 + cidx;
+    dst[off] = round_tf32(src[off] * factor[slot]);
+  }
+}
+
+// out[m][c][kh][kw] (+)= T[m][kh][kw*C + c]
+__global__ void permute_accum_kernel(const float* __restrict__ T, float* __restrict__ out, int M, int C, int KH,
+                                     int KW, int accumulate) {
+  const long long total = static_cast<long long>(M) * C * KH * KW;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    // i enumerates the destination (coalesced writes); reads are strided but L2 resident
+    const int kw = static_cast<int>(i % KW);
+    long long t = i / KW;
+    const int kh = static_cast<int>(t % KH);
+    t /= KH;
+    const int c = static_cast<int>(t % C);
+    const int m = static_cast<int>(t / C);
+    const float v = T[(static_cast<long long>(m) * KH + kh) * (static_cast<long long>(KW) * C) + static_cast<long long>(kw) * C + c];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+
+// out[r] (+)= sum_slot factor[slot] * rows_in[slot*R + r]; one thread per r, slots split over blockIdx.y
+__global__ void weighted_colsum_kernel(const float* __restrict__ rows_in, const float* __restrict__ factor,
+                                       int slot_lo, int slot_hi, int R, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int per = (slot_hi - slot_lo + gridDim.y - 1) / gridDim.y;
+  const int lo = slot_lo + blockIdx.y * per;
+  const int hi = min(lo + per, slot_hi);
+  float acc = 0.f;
+  for (int s = lo; s < hi; ++s) acc = fmaf(factor[s], rows_in[static_cast<long long>(s) * R + r], acc);
+  if (hi > lo) atomicAdd(out + r, acc);
+}
+
+__global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int n_slots, int slot_lo, int slot_hi,
+                                int stat, float scalar, float* __restrict__ out) {
+  __shared__ float sh[32];
+  const int k = blockIdx.x;
+  const float* row = norms + static_cast<long long>(k) * n_slots;
+  float acc = stat ? -INFINITY : 0.f;
+  for (int s = slot_lo + threadIdx.x; s < slot_hi; s += blockDim.x) acc = stat ? fmaxf(acc, row[s]) : acc + row[s];
+  if (stat) {
+    acc = warp_max(acc);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      acc = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -INFINITY;
+      acc = warp_max(acc);
+    }
+  } else {
+    acc = block_sum(acc, sh);
+    acc /= static_cast<float>(slot_hi - slot_lo);
+  }
+  if (threadIdx.x == 0) out[k] = acc * scalar;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox noise, bit-compatible with torch's CUDA normal_ (see header comment of the ABI)
+// launched with exactly torch's geometry: block 256, grid = min(SMs*(maxThreads/256), ceil(n/256))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+noise_finalize_kernel(const float* in, float* grad, long long numel, float in_div, float stdv, float noise_div,
+                      unsigned long long seed, unsigned long long offset, const float* __restrict__ std_dev) {
+  if (std_dev) stdv = __fmul_rn(stdv, std_dev[0]);
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  curandStatePhilox4_32_10_t state;
+  curand_init(seed, idx, offset, &state);
+  const long long nthreads = static_cast<long long>(blockDim.x) * gridDim.x;
+  const long long rounded = ((numel - 1) / (nthreads * 4) + 1) * nthreads * 4;
+  for (long long li0 = idx; li0 < rounded; li0 += nthreads * 4) {
+    const float4 z = curand_normal4(&state);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const long long li = li0 + nthreads * ii;
+      if (li < numel) {
+        float nz = __fmul_rn(zz[ii], stdv);                 // torch.normal(0, std): rand * std + 0
+        if (noise_div > 0.f) nz = __fdiv_rn(nz, noise_div);  // noise /= batch_size
+        float g = 0.f;
+        if (in) {
+          g = in[li];
+          if (in_div > 0.f) g = __fdiv_rn(g, in_div);        // p.grad = summed_grad / batch_size
+          g = __fadd_rn(g, nz);                              // p.grad += noise
+        } else {
+          g = nz;
+        }
+        grad[li] = g;
+      }
+    }
+  }
+}
+
+// no-noise variant (sigma == 0 or C == 0): grad = in / in_div
+__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float div) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = div > 0.f ? __fdiv_rn(in[i], div) : in[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// row-norm backward, vector max, fused per-sample L2 clip
+// ------------------------------------------------------------------------------------------
+__global__ void row_l2_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norms,
+                                       const float* __restrict__ gout, long long rows, long long cols,
+                                       float* __restrict__ gin) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float n = norms[r];
+    const float s = n > 0.f ? gout[r] / n : 0.f;
+    const float* gr = g + r * cols;
+    float* o = gin + r * cols;
+    for (long long i = threadIdx.x; i < cols; i += blockDim.x) o[i] = gr[i] * s;
+  }
+}
+
+__global__ void vec_max_kernel(const float* __restrict__ v, long long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float acc = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc = fmaxf(acc, v[i]);
+  acc = warp_max(acc);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -INFINITY;
+    acc = warp_max(acc);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+
+// one block per row: norm, then out = norm > C ? C * (t / norm) : t   (same op order as the reference)
+__global__ void l2_clip_kernel(const float* __restrict__ t, long long rows, long long cols, float C,
+                               float* __restrict__ out, float* __restrict__ norms_out) {
+  __shared__ float sh[32];
+  __shared__ float s_norm;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = t + r * cols;
+    float s = block_sum(row_sumsq_device(row, cols), sh);
+    if (threadIdx.x == 0) {
+      s_norm = sqrtf(s);
+      if (norms_out) norms_out[r] = s_norm;
+    }
+    __syncthreads();
+    const float n = s_norm;
+    float* o = out + r * cols;
+    if (n > C) {
+      for (long long i = threadIdx.x; i < cols; i += blockDim.x) o[i] = __fmul_rn(C, __fdiv_rn(row[i], n));
+    } else {
+      for (long long i = threadIdx.x; i < cols; i += blockDim.x) o[i] = row[i];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace cg

@@ -1,0 +1,637 @@
+"""PrivacyEngine: the gc (per-sample gradient clipping) engine behind `--dp_mode gc`.
+
+Drop-in for the twosixlabs/opacus fork's `PrivacyEngine` as reference train.py drives it
+(constructor train.py:110-116; attach/_set_seed :135-136; enable/disable_hooks :117, 373, 389;
+clip :399; accum_grads_across_passes :402; accumulate_batch :417/450/467; set_max_grad_norm
+:241-243; clipper.* and calc_sample_norms :311-328; patched optimizer.step :484; get_privacy_spent
+:295, 588).  The arithmetic runs in hand-written sm_100a kernels behind the C ABI
+(include/cslgan_b200.h); this module is host-side bookkeeping only and has no fallback path.
+
+Pipeline per D step (all on the current CUDA stream, no host synchronisation):
+  forward hooks   stage activations (TF32, K-major / kw-plane layout)
+  tensor hooks    stage B * grad_output, per-sample bias gradients, Linear ||b||^2
+  clip()          per-sample squared norms  (tcgen05 contraction with a sum-of-squares epilogue;
+                  closed form ||a||^2 ||b||^2 for Linear)  ->  clip factors  ->  clip-factor-scaled
+                  backprops  ->  ONE split-K tcgen05 GEMM per layer over all samples and passes
+  accumulate_batch()  p.summed_grad (+)= clipped sums
+  optimizer.step()    p.grad = summed/B + Philox N(0, (sigma C_k)^2)/B   (bit-compatible with torch)
+
+Fork semantics that cannot be verified here are explicit switches: see
+`split_clip_fake`, `noise_on`, and DESIGN.md.
+"""
+from __future__ import annotations
+
+import types
+from itertools import cycle
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .accountant import get_privacy_spent as _rdp_to_eps, compute_rdp
+from .grad_sample import LayerPlan, _round_up
+
+SUPPORTED_LAYERS = (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)
+_UNSUPPORTED_WITH_PARAMS = (nn.modules.batchnorm._BatchNorm,)
+
+
+class GradSampleView:
+    """Lazy stand-in for `p.grad_sample` ([n_passes, B, *p.shape], reference train.py:233, 388, 447).
+
+    The tensor is never materialised for the accesses the reference makes on the hot path:
+      p.grad_sample.size(1)                                    -> batch size
+      p.grad_sample[k].view(B, -1).norm(2, dim=1)              -> fused per-sample norms
+    Anything else (`.materialize()`, `torch.as_tensor`-style use) runs the store epilogue.
+    """
+
+    def __init__(self, engine: "PrivacyEngine", p_idx: int):
+        self._e, self._k = engine, p_idx
+
+    @property
+    def shape(self):
+        e = self._e
+        return torch.Size((e._n_passes_view(), e._cur_B) + tuple(e._params[self._k].shape))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return len(self.shape)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, int):
+            return _PassView(self, idx)
+        return self.materialize()[idx]
+
+    def materialize(self) -> torch.Tensor:
+        return self._e.materialize_grad_sample(self._k)
+
+    def __torch_function__(self, func, types_, args=(), kwargs=None):  # pragma: no cover - convenience
+        args = tuple(a.materialize() if isinstance(a, GradSampleView) else a for a in args)
+        return func(*args, **(kwargs or {}))
+
+
+class _PassView:
+    def __init__(self, gs: GradSampleView, pass_idx: int):
+        self._gs, self._p = gs, pass_idx
+
+    def view(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        if len(shape) == 2 and shape[1] == -1:
+            return _FlatView(self._gs, self._p)
+        return self.materialize().view(*shape)
+
+    reshape = view
+
+    def materialize(self):
+        return self._gs.materialize()[self._p]
+
+
+class _FlatView:
+    def __init__(self, gs: GradSampleView, pass_idx: int):
+        self._gs, self._p = gs, pass_idx
+
+    def norm(self, p=2, dim=1, **kw):
+        if p != 2 or dim not in (1, -1):
+            return self._gs.materialize()[self._p].flatten(1).norm(p, dim=dim, **kw)
+        e = self._gs._e
+        return e.per_sample_norms()[self._gs._k, self._p]
+
+
+class _NormClipperShim:
+    """`privacy_engine.clipper.norm_clipper` (reference train.py:313, 324)."""
+
+    def __init__(self, engine: "PrivacyEngine"):
+        self._e = engine
+
+    @property
+    def is_per_layer(self) -> bool:
+        return self._e.is_per_layer
+
+    @property
+    def thresholds(self) -> torch.Tensor:
+        return self._e._thresholds_dev.clone()
+
+    def calc_clipping_factors(self, norms=None):
+        """Iterable of [n_passes, B] factors, one per parameter (flat: the same vector cycled,
+        like upstream ConstantFlatClipper)."""
+        f = self._e.clipping_factors()
+        if self._e.is_per_layer:
+            return [f[k] for k in range(f.shape[0])]
+        return cycle([f[0]])
+
+
+class _ClipperShim:
+    """`privacy_engine.clipper` (reference train.py:312-313)."""
+
+    def __init__(self, engine: "PrivacyEngine"):
+        self._e = engine
+        self.norm_clipper = _NormClipperShim(engine)
+
+    def _named_grad_samples(self):
+        e = self._e
+        return [(n, GradSampleView(e, k)) for k, n in enumerate(e._param_names)]
+
+    def _named_params(self):
+        return list(zip(self._e._param_names, self._e._params))
+
+
+def calc_sample_norms(named_params, flat: bool = True) -> List[torch.Tensor]:
+    """`opacus.utils.tensor_utils.calc_sample_norms` (reference train.py:311-314) with the fork's
+    pass dimension: items are [n_passes, B]; flat -> one item with the norm across parameters."""
+    named_params = list(named_params)
+    views = [v for _, v in named_params]
+    if views and all(isinstance(v, GradSampleView) for v in views):
+        e = views[0]._e
+        per = e.per_sample_norms()                      # [n_params, n_passes, B]
+        ks = [v._k for v in views]
+        if flat:
+            if ks == list(range(per.shape[0])):
+                return [e.flat_sample_norms()]
+            return [per[ks].norm(2, dim=0)]
+        return [per[k] for k in ks]
+    norms = [p.reshape(p.shape[0], p.shape[1], -1).norm(2, dim=-1) for _, p in named_params]
+    if flat:
+        norms = [torch.stack(norms, dim=0).norm(2, dim=0)]
+    return norms
+
+
+class PrivacyEngine:
+    def __init__(self, module: nn.Module, *, batch_size: int, sample_size: int,
+                 alphas: Sequence[float] = tuple([1 + x / 10.0 for x in range(1, 100)] + list(range(12, 64))),
+                 noise_multiplier: float, max_grad_norm: Union[float, Sequence[float], torch.Tensor],
+                 accum_passes: bool = False, num_private_passes: Optional[int] = None,
+                 auto_clip_and_accum_on_step: bool = True, loss_reduction: str = "mean",
+                 split_clip_fake: bool = True, max_passes: int = 2, process_group=None,
+                 data_parallel: bool = False, **misc):
+        if loss_reduction not in ("mean", "sum"):
+            raise ValueError("loss_reduction must be 'mean' or 'sum'")
+        L.load()                                          # fail loudly, now, if the CUDA library is absent
+        self.module = module
+        self.batch_size = batch_size
+        self.sample_size = sample_size
+        self.sample_rate = batch_size / sample_size
+        self.alphas = list(alphas)
+        self.noise_multiplier = float(noise_multiplier)
+        self.accum_passes = accum_passes
+        self.num_private_passes = num_private_passes
+        self.auto_clip_and_accum_on_step = auto_clip_and_accum_on_step
+        self.loss_reduction = loss_reduction
+        self.split_clip_fake = split_clip_fake
+        self.max_passes = max_passes
+        self.process_group = process_group
+        self.data_parallel = data_parallel or process_group is not None
+        self.misc_settings = misc
+        self.steps = 0
+        self.hooks_enabled = True
+        self.optimizer = None
+        self.validate()
+
+        self._params: List[nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
+        names = {id(p): n for n, p in module.named_parameters()}
+        self._param_names = [names[id(p)] for p in self._params]
+        pidx = {id(p): k for k, p in enumerate(self._params)}
+        self.device = self._params[0].device
+        if self.device.type != "cuda":
+            raise L.CslGanCudaError(
+                f"PrivacyEngine needs the module on a CUDA device (found {self.device}); there is no CPU path")
+        self._plans: List[LayerPlan] = []
+        covered = set()
+        for name, layer in module.named_modules():
+            if isinstance(layer, SUPPORTED_LAYERS):
+                own = [p for p in layer.parameters(recurse=False) if p.requires_grad]
+                if not own:
+                    continue
+                w = pidx[id(layer.weight)]
+                b = pidx[id(layer.bias)] if getattr(layer, "bias", None) is not None and layer.bias.requires_grad else None
+                self._plans.append(LayerPlan(name, layer, w, b))
+                covered.update(id(p) for p in own)
+        missing = [n for n, p in zip(self._param_names, self._params) if id(p) not in covered]
+        if missing:
+            raise NotImplementedError(f"parameters outside Linear/Conv2d/ConvTranspose2d layers: {missing}")
+        self._handles = []
+        for plan in self._plans:
+            self._handles.append(plan.layer.register_forward_hook(self._make_fwd_hook(plan)))
+
+        self.Bpad = _round_up(batch_size, 32)
+        self._alloc_state()
+        self.set_max_grad_norm(max_grad_norm)
+        self.clipper = _ClipperShim(self)
+        self._seed = 0
+        self._philox_offset = 0
+        self._set_seed(int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
+        self._reset_capture()
+        self._accum_bs = 0
+        self._clipped: Optional[List[torch.Tensor]] = None
+        self._sm_count = L.device_info()[0]
+
+    # ------------------------------------------------------------------ validation / attach
+    def validate(self):
+        """Upstream attach() refuses modules it cannot compute per-sample gradients for."""
+        for name, m in self.module.named_modules():
+            if isinstance(m, _UNSUPPORTED_WITH_PARAMS):
+                raise NotImplementedError(f"{name}: BatchNorm is incompatible with per-sample gradients")
+
+    def attach(self, optimizer: torch.optim.Optimizer):
+        """Patch optimizer.step / zero_grad like upstream PrivacyEngine.attach (reference train.py:135)."""
+        self.optimizer = optimizer
+        engine = self
+
+        def dp_step(opt_self, closure=None):
+            engine.step()
+            return opt_self.original_step(closure)
+
+        def dp_zero_grad(opt_self, *a, **k):
+            engine.zero_grad()
+            return opt_self.original_zero_grad(*a, **k)
+
+        def virtual_step(opt_self):
+            engine.virtual_step()
+
+        optimizer.privacy_engine = self
+        optimizer.original_step = optimizer.step
+        optimizer.step = types.MethodType(dp_step, optimizer)
+        optimizer.original_zero_grad = optimizer.zero_grad
+        optimizer.zero_grad = types.MethodType(dp_zero_grad, optimizer)
+        optimizer.virtual_step = types.MethodType(virtual_step, optimizer)
+
+    def detach(self):
+        opt = self.optimizer
+        if opt is not None:
+            opt.step = opt.original_step
+            opt.zero_grad = opt.original_zero_grad
+            del opt.privacy_engine, opt.original_step, opt.original_zero_grad, opt.virtual_step
+            self.optimizer = None
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _set_seed(self, seed: int):
+        """Seed the engine's private Philox stream (upstream: a private torch.Generator on the
+        device; reference train.py:136).  State = (seed, offset) exactly like a CUDA generator."""
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._philox_offset = 0
+
+    # checkpointing of the engine state the reference forgets (accountant restarts on resume)
+    def state_dict(self) -> Dict:
+        return {"steps": self.steps, "seed": self._seed, "philox_offset": self._philox_offset,
+                "max_grad_norm": self.max_grad_norm}
+
+    def load_state_dict(self, sd: Dict):
+        self.steps = sd["steps"]
+        self._seed, self._philox_offset = sd["seed"], sd["philox_offset"]
+        self.set_max_grad_norm(sd["max_grad_norm"])
+
+    # ------------------------------------------------------------------ hooks
+    def enable_hooks(self):
+        self.hooks_enabled = True
+
+    def disable_hooks(self):
+        self.hooks_enabled = False
+
+    def _make_fwd_hook(self, plan: LayerPlan):
+        def fwd_hook(layer, inputs, output):
+            if not self.hooks_enabled or not torch.is_grad_enabled():
+                return
+            pass_idx = self._pass_count.get(plan, 0)
+            if pass_idx >= self.max_passes:
+                raise RuntimeError(
+                    f"{plan.name}: more than max_passes={self.max_passes} forward passes captured before clip()")
+            act = inputs[0]
+            B = act.shape[0]
+            if B > self.Bpad:
+                self.Bpad = _round_up(B, 32)
+                self._alloc_state()
+            self._pass_count[plan] = pass_idx + 1
+            self._pass_B[pass_idx] = B
+            self._cur_B = B
+            plan.capture_activation(act, pass_idx, self.Bpad, self.max_passes)
+            self._norms_valid = False
+            self._factors_valid = False
+            if output.requires_grad:
+                scale = float(B) if self.loss_reduction == "mean" else 1.0
+
+                def grad_hook(g, plan=plan, pass_idx=pass_idx, scale=scale):
+                    if self.hooks_enabled:
+                        plan.capture_backprop(g, pass_idx, scale)
+                        self._bp_seen.add((plan, pass_idx))
+
+                output.register_hook(grad_hook)
+        return fwd_hook
+
+    def _reset_capture(self):
+        self._pass_count: Dict[LayerPlan, int] = {}
+        self._pass_B: Dict[int, int] = {}
+        self._bp_seen = set()
+        self._cur_B = self.batch_size
+        self._norms_valid = False
+        self._factors_valid = False
+
+    def _n_passes(self) -> int:
+        return max(self._pass_count.values(), default=0)
+
+    def _n_passes_view(self) -> int:
+        return 1 if self.accum_passes else max(self._n_passes(), 1)
+
+    def _alloc_state(self):
+        S = self.Bpad * self.max_passes
+        n = len(self._params)
+        dev = self.device
+        self._S = S
+        self._norm2 = torch.zeros((n, S), device=dev)
+        self._norms = torch.zeros((n, S), device=dev)
+        self._flat_norms = torch.zeros((1, S), device=dev)
+        self._factors = torch.ones((n, S), device=dev)
+        for plan in getattr(self, "_plans", []):
+            plan.ready = False
+
+    # ------------------------------------------------------------------ thresholds
+    @property
+    def is_per_layer(self) -> bool:
+        return self._per_layer
+
+    def set_max_grad_norm(self, v):
+        """float -> flat clipping; list -> per-layer C_k; tensors stay on the device (reference
+        train.py:241 passes a list, :243 a 0-dim tensor)."""
+        n = len(self._params)
+        if isinstance(v, torch.Tensor):
+            if v.dim() == 0:
+                self._per_layer = False
+                self._thresholds_dev = v.detach().to(self.device, torch.float32).reshape(1).clone()
+                self.max_grad_norm = v
+                self._thresholds_host = None
+                return
+            self._per_layer = True
+            t = v.detach().to(self.device, torch.float32).reshape(-1)
+            if t.numel() == 1:
+                t = t.repeat(n)
+            if t.numel() != n:
+                raise ValueError(f"expected {n} per-layer thresholds, got {t.numel()}")
+            self._thresholds_dev = t.clone()
+            self.max_grad_norm = v
+            self._thresholds_host = None
+            return
+        if isinstance(v, (list, tuple)):
+            vals = [float(x) for x in v]
+            if len(vals) == 1:
+                vals = vals * n
+            if len(vals) != n:
+                raise ValueError(f"expected {n} per-layer thresholds, got {len(vals)}")
+            self._per_layer = True
+            self.max_grad_norm = list(v)
+        else:
+            vals = [float(v)]
+            self._per_layer = False
+            self.max_grad_norm = float(v)
+        self._thresholds_host = vals
+        self._thresholds_dev = torch.tensor(vals, dtype=torch.float32, device=self.device)
+        self._factors_valid = False
+
+    # ------------------------------------------------------------------ norms / factors
+    def _check_captured(self):
+        np_ = self._n_passes()
+        if np_ == 0:
+            raise RuntimeError("no per-sample gradients captured: run forward/backward with hooks enabled first")
+        return np_
+
+    def _compute_norms(self):
+        if self._norms_valid:
+            return
+        n_passes = self._check_captured()
+        if self.accum_passes and n_passes > 1:
+            raise NotImplementedError(
+                "accum_passes=True (joint clipping of fake_i + real_i, -gcs False) is not implemented yet; "
+                "use the reference default grad_clip_split=True")
+        self._norm2.zero_()
+        joint = 1
+        for plan in self._plans:
+            passes = range(1) if self.accum_passes else range(self._pass_count.get(plan, 0))
+            for ps in passes:
+                if not self.accum_passes and (plan, ps) not in self._bp_seen:
+                    continue                       # layer got no backprop in this pass -> zero gradient
+                B = self._pass_B[ps]
+                plan.weight_norm2(self._norm2[plan.w_idx], ps, B, joint)
+                if plan.b_idx is not None:
+                    if joint != 1:
+                        raise NotImplementedError("accum_passes=True bias norms")
+                    plan.bias_norm2(self._norm2[plan.b_idx], ps, B)
+        self._norms_valid = True
+        self._factors_valid = False
+
+    def _compute_factors(self):
+        self._compute_norms()
+        if self._factors_valid:
+            return
+        n = len(self._params)
+        S = self._S
+        clip_lo, clip_hi = 0, S
+        if (not self.accum_passes) and (not self.split_clip_fake) and self.num_private_passes is not None:
+            clip_lo = (self._n_passes() - self.num_private_passes) * self.Bpad
+        st = L.stream_ptr(self.device)
+        if self._per_layer:
+            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 1, L.ptr(self._thresholds_dev), clip_lo, clip_hi,
+                   L.ptr(self._factors), L.ptr(self._norms), st)
+        else:
+            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 0, L.ptr(self._thresholds_dev), clip_lo, clip_hi,
+                   L.ptr(self._factors), L.ptr(self._flat_norms), st)
+        self._factors_valid = True
+
+    def _slot_view(self, t: torch.Tensor) -> torch.Tensor:
+        """[rows, S] -> [rows, n_passes, B] view over the live slots."""
+        np_ = self._n_passes_view()
+        return t.view(t.shape[0], self.max_passes, self.Bpad)[:, :np_, :self._cur_B]
+
+    def per_sample_norms(self) -> torch.Tensor:
+        """[n_params, n_passes, B] per-parameter per-sample L2 norms (device tensor, no sync)."""
+        self._compute_norms()
+        return self._slot_view(self._norm2).sqrt()
+
+    def flat_sample_norms(self) -> torch.Tensor:
+        """[n_passes, B] norms across all parameters."""
+        self._compute_norms()
+        return self._slot_view(self._norm2).sum(dim=0).sqrt()
+
+    def clipping_factors(self) -> torch.Tensor:
+        """[n_params or 1, n_passes, B]."""
+        self._compute_factors()
+        rows = self._factors if self._per_layer else self._factors[:1]
+        return self._slot_view(rows)
+
+    def adaptive_thresholds(self, stat: str = "mean", scalar: float = 1.5, pass_idx: int = 0) -> torch.Tensor:
+        """Per-parameter mean/max of the per-sample norms of one pass times `scalar`, as a DEVICE
+        tensor (reference train.py:230-243 does this with one .cpu().item() sync per parameter)."""
+        self._compute_norms()
+        n = len(self._params)
+        norms = self._norm2.sqrt()
+        out = torch.empty(n, device=self.device)
+        lo = pass_idx * self.Bpad
+        L.call("cg_row_stat", L.ptr(norms), n, self._S, lo, lo + self._pass_B.get(pass_idx, self._cur_B),
+               1 if stat == "max" else 0, float(scalar), L.ptr(out), L.stream_ptr(self.device))
+        return out
+
+    def materialize_grad_sample(self, p_idx: int) -> torch.Tensor:
+        """[n_passes, B, *p.shape] (rare path; reference train.py:447 and tests)."""
+        n_passes = self._check_captured()
+        p = self._params[p_idx]
+        outs = []
+        for plan in self._plans:
+            if plan.w_idx == p_idx:
+                for ps in range(n_passes):
+                    B = self._pass_B[ps]
+                    if (plan, ps) in self._bp_seen:
+                        outs.append(plan.materialize(ps, B))
+                    else:
+                        outs.append(torch.zeros((B,) + tuple(p.shape), device=self.device))
+            elif plan.b_idx == p_idx:
+                for ps in range(n_passes):
+                    B = self._pass_B[ps]
+                    lo = ps * self.Bpad
+                    outs.append(plan.bias_rows[lo:lo + B].clone() if (plan, ps) in self._bp_seen
+                                else torch.zeros((B,) + tuple(p.shape), device=self.device))
+        g = torch.stack(outs, dim=0)
+        if self.accum_passes:
+            g = g.sum(dim=0, keepdim=True)
+        return g
+
+    # ------------------------------------------------------------------ clip / accumulate / step
+    def clip(self):
+        """norms -> factors -> clipped weighted sum (reference train.py:399).  The per-pass sums of
+        split mode are produced already added together; accum_grads_across_passes() is then a no-op."""
+        n_passes = self._check_captured()
+        self._compute_factors()
+        outs = [torch.empty_like(p) for p in self._params]
+        slot_hi = (n_passes - 1) * self.Bpad + self._pass_B[n_passes - 1]
+        for plan in self._plans:
+            live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
+            if not live:
+                outs[plan.w_idx].zero_()
+                if plan.b_idx is not None:
+                    outs[plan.b_idx].zero_()
+                continue
+            if len(live) == n_passes:
+                ranges = [(0, slot_hi)]
+            else:
+                ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps]) for ps in live]
+            frow_w = self._factors[plan.w_idx if self._per_layer else 0]
+            for i, (lo, hi) in enumerate(ranges):
+                plan.scale_backprops(frow_w, lo, hi)
+                plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0)
+                if plan.b_idx is not None:
+                    frow_b = self._factors[plan.b_idx if self._per_layer else 0]
+                    plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=i > 0)
+        self._clipped = outs
+        return outs
+
+    def accum_grads_across_passes(self):
+        """Sum the per-pass clipped sums (reference train.py:402).  Already fused into clip()."""
+        if self._clipped is None:
+            raise RuntimeError("accum_grads_across_passes() called before clip()")
+
+    def accumulate_batch(self):
+        """p.summed_grad (+)= clipped sum; a SUM, not a mean (reference train.py:417, 431)."""
+        if self._clipped is None:
+            raise RuntimeError("accumulate_batch() called before clip()")
+        for p, c in zip(self._params, self._clipped):
+            if getattr(p, "summed_grad", None) is None:
+                p.summed_grad = c
+            else:
+                p.summed_grad.add_(c)
+        # only the private pass counts towards the batch size (both passes hold the same B)
+        self._accum_bs += self._cur_B
+        self._clipped = None
+        self._reset_capture()
+        self._drop_grad_sample_attrs()
+
+    def _drop_grad_sample_attrs(self):
+        for p in self._params:
+            if hasattr(p, "grad_sample"):
+                del p.grad_sample
+
+    def expose_grad_sample_attrs(self):
+        """Attach the lazy `p.grad_sample` views (reference train.py:233, 388 read them)."""
+        for k, p in enumerate(self._params):
+            p.grad_sample = GradSampleView(self, k)
+
+    def noise_stds(self) -> List[float]:
+        th = self._thresholds_host
+        if th is None:
+            raise RuntimeError("thresholds live on the device")
+        cs = th if self._per_layer else th * len(self._params)
+        return [self.noise_multiplier * c for c in cs]
+
+    def virtual_step(self):
+        self.clip()
+        self.accumulate_batch()
+
+    def step(self):
+        """Engine half of the patched optimizer.step() (reference train.py:484): p.grad = summed/B,
+        noise = N(0, (sigma*C_k)^2) drawn per parameter tensor from the Philox stream, noise /= B
+        (mean reduction), p.grad += noise."""
+        if self.auto_clip_and_accum_on_step and self._n_passes() > 0:
+            self.clip()
+            self.accumulate_batch()
+        if self._accum_bs == 0:
+            raise ValueError("No accumulated gradients: call clip()/accumulate_batch() before step()")
+        self.steps += 1
+        bs = float(self._accum_bs)
+        if self.data_parallel:
+            bs = self._allreduce_summed(bs)
+        div = bs if self.loss_reduction == "mean" else 0.0
+        st = L.stream_ptr(self.device)
+        inc = C.c_ulonglong(0)
+        host = self._thresholds_host
+        for k, p in enumerate(self._params):
+            s = p.summed_grad
+            g = torch.empty_like(p)
+            if host is not None:
+                std = self.noise_multiplier * (host[k] if self._per_layer else host[0])
+                L.call("cg_noise_finalize", L.ptr(s), L.ptr(g), s.numel(), div, std, div,
+                       self._seed, self._philox_offset, C.byref(inc), st)
+            else:
+                cdev = self._thresholds_dev[k:k + 1] if self._per_layer else self._thresholds_dev[:1]
+                L.call("cg_noise_finalize_dev", L.ptr(s), L.ptr(g), s.numel(), div, self.noise_multiplier,
+                       L.ptr(cdev), div, self._seed, self._philox_offset, C.byref(inc), st)
+            self._philox_offset += inc.value
+            p.grad = g
+            p.summed_grad = None
+        self._accum_bs = 0
+
+    def _allreduce_summed(self, bs: float) -> float:
+        """Data parallel: one NCCL allreduce(SUM) of the flattened clipped sums; the batch size is
+        the global one; noise is then drawn identically on every rank from the shared Philox
+        (seed, offset), so all replicas apply the same update."""
+        import torch.distributed as dist
+        pg = self.process_group
+        flat = torch.cat([p.summed_grad.reshape(-1) for p in self._params])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
+        off = 0
+        for p in self._params:
+            n = p.numel()
+            p.summed_grad = flat[off:off + n].view_as(p)
+            off += n
+        return bs * dist.get_world_size(pg)
+
+    def zero_grad(self):
+        """Patched optimizer.zero_grad (reference train.py:245): also drops captured state."""
+        self._reset_capture()
+        self._clipped = None
+        self._drop_grad_sample_attrs()
+
+    # ------------------------------------------------------------------ accountant
+    def get_renyi_divergence(self):
+        return compute_rdp(self.sample_rate, self.noise_multiplier, 1, self.alphas)
+
+    def get_privacy_spent(self, target_delta: Optional[float] = None) -> Tuple[float, float]:
+        """(epsilon, best alpha) after `self.steps` steps (reference train.py:295, 588;
+        budget_analysis.py:79-80 also assigns `.steps` directly)."""
+        if target_delta is None:
+            target_delta = self.misc_settings.get("target_delta", 1e-6)
+        rdp = compute_rdp(self.sample_rate, self.noise_multiplier, self.steps, self.alphas)
+        return _rdp_to_eps(self.alphas, rdp, target_delta)

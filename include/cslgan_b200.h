@@ -1,0 +1,219 @@
+/*
+ * cslgan_b200.h -- C ABI of the B200-native DP discriminator-update hot path.
+ *
+ * The reference (twosixlabs/csl-gan) has no native boundary: train.py talks to a Python
+ * object protocol (the twosixlabs/opacus fork's PrivacyEngine / ISPrivacyEngine,
+ * reference requirements.txt:9, train.py:13-14).  This header is the native seam a
+ * maintainer binds *underneath* that protocol: each entry point replaces one piece of
+ * tensor arithmetic the fork performs with ATen ops, and the comment on each one cites
+ * the reference call site (reference file:line) and the upstream-opacus op it replaces.
+ * INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: raw device pointers (fp32 unless noted), sizes, a cudaStream_t passed as
+ *     void*.  No torch types.  All work is enqueued on `stream`; nothing synchronises.
+ *   - every function returns 0 on success, non-zero on failure; cg_last_error() returns a
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - there is NO CPU fallback: without a CUDA device / the sm_100a cubin every call fails.
+ *
+ * Vocabulary
+ *   slot      one (pass, sample) pair: slot = pass * B + n.  Passes are D forward calls in
+ *             forward order (0 = fake, 1 = real in train.py:382-383).
+ *   X operand "plain" side of a layer's per-sample contraction, staged K-major:
+ *             X[r][slot * x_slot_stride + q]   (Conv2d/Linear: backprops, r = out channel)
+ *   Y operand "unfolded" side, staged as kw-planes so that every filter tap is a shifted
+ *             window of a plain 2-D matrix (no im2col blow-up beyond KW * n_rho / (sh*sw)):
+ *             Y[(j*KW + kw)*C + c][slot * y_slot_stride + hs*Wo + ow]
+ *   per-sample gradient of a layer  G_slot[m][c][kh][kw] = sum_q X[m][slot,q] * Y_tap[c][slot,q]
+ */
+#ifndef CSLGAN_B200_H
+#define CSLGAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_MAX_KH 16
+
+typedef void* cg_stream_t; /* cudaStream_t */
+
+int cg_version(void);
+const char* cg_last_error(void);
+/* SM count / max threads per SM of the current device (used for the torch-compatible Philox grid). */
+int cg_device_info(int* sm_count, int* max_threads_per_sm, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Geometry of the unfolded operand of one layer (Conv2d: the layer input; ConvTranspose2d: the
+ * grad wrt the layer output; Linear: KH=KW=1, H=W=Ho=Wo=1, C = in_features).
+ * Replaces F.unfold(A, kernel, padding, stride, dilation) in upstream opacus
+ * `_compute_conv_grad_sample` (fired from reference train.py:387 d_loss.backward()).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cg_unfold_geom {
+  int C, H, W;          /* source tensor [B][C][H][W]                                  */
+  int KH, KW;           /* filter taps                                                 */
+  int sh, sw, ph, pw, dh, dw; /* stride / padding / dilation                           */
+  int Ho, Wo;           /* number of window positions (contraction length Q = Ho*Wo)   */
+} cg_unfold_geom;
+
+/* Derived staging layout, filled by cg_plan_unfold(). */
+typedef struct cg_unfold_plan {
+  int n_rho;                 /* distinct row residues (kh*dh - ph) mod sh               */
+  int Hs;                    /* staged rows per plane = Ho + a_max - a_min              */
+  int rows;                  /* staged matrix rows = n_rho * KW * C                     */
+  int slot_stride;           /* columns per slot = Hs * Wo                              */
+  int tap_row0[CG_MAX_KH];   /* first staged row of tap-group kh  (= j(kh) * KW * C)    */
+  int tap_coloff[CG_MAX_KH]; /* column offset of tap-group kh     (= (a(kh)-a_min)*Wo)  */
+  int rho[CG_MAX_KH];        /* residue value of plane j                                */
+  int a_min;
+} cg_unfold_plan;
+
+int cg_plan_unfold(const cg_unfold_geom* g, cg_unfold_plan* plan);
+
+/* ---------------------------------------------------------------------------------------------
+ * Capture (replaces the fork's forward/backward hook bodies: upstream _capture_activations and
+ * _compute_{linear,conv}_grad_sample; hooks are armed by enable_hooks(), reference train.py:373).
+ * All staged values are rounded to TF32 (round-to-nearest) so the tensor cores see unbiased
+ * operands.
+ * ------------------------------------------------------------------------------------------- */
+
+/* src [B][R] (Linear activations or backprops) -> dst[r][slot0+n] = tf32(scale*src[n][r]).
+ * Optional: copy_out[(slot0+n)*R + r] = scale*src (fp32, un-rounded: per-sample bias gradients),
+ *           sumsq[slot0+n] = sum_r (scale*src[n][r])^2 (closed-form Linear norms ||a||^2, ||b||^2). */
+int cg_stage_rows_t(const float* src, int B, int R, float scale, float* dst, long long dst_pitch,
+                    int slot0, float* copy_out, float* sumsq, cg_stream_t stream);
+
+/* src [B][R][Q] (conv backprops; ConvTranspose2d activations) ->
+ *   dst[r][(slot0+n)*Qpad + q] = tf32(scale*src[n][r][q]), zero for Q <= q < Qpad.
+ * Optional rowsum[(slot0+n)*R + r] = scale * sum_q src[n][r][q]  (per-sample bias gradients,
+ *   upstream torch.sum(B, dim=2)). */
+int cg_stage_rows(const float* src, int B, int R, int Q, int Qpad, float scale, float* dst,
+                  long long dst_pitch, int slot0, float* rowsum, cg_stream_t stream);
+
+/* src [B][C][H][W] -> kw-plane matrix (see cg_unfold_plan), zero padding materialised. */
+int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_unfold_plan* plan,
+                    float scale, float* dst, long long dst_pitch, int slot0, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The per-sample contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * One persistent kernel, three epilogues:
+ *   CG_EPI_SUMSQ  norm2[group] += sum of squares of the group's gradient tile
+ *                 -> per-sample squared norms without materialising B x |theta|
+ *                 (replaces calc_sample_norms, reference train.py:311-314, and the norm pass
+ *                  inside privacy_engine.clip(), train.py:399)
+ *   CG_EPI_ACCUM  out[m][kh][kw*C+c] += tile  (clipped weighted sum as ONE split-K GEMM over
+ *                 all slots with clip-factor-scaled X; replaces upstream _weighted_sum
+ *                 einsum("i,i...", cf, grad_sample) inside clip(), train.py:399)
+ *   CG_EPI_STORE  out[group][m][c][kh][kw] = tile (materialise grad_sample for the rare
+ *                 consumers: train.py:233, 447 and tests)
+ * ------------------------------------------------------------------------------------------- */
+enum { CG_EPI_SUMSQ = 0, CG_EPI_ACCUM = 1, CG_EPI_STORE = 2 };
+enum { CG_GROUP_SAMPLE = 0, CG_GROUP_SPLITK = 1 };
+
+typedef struct cg_contract_desc {
+  const float* X; long long x_pitch; int x_rows; long long x_cols; /* [x_rows][x_cols], pitch in floats */
+  const float* Y; long long y_pitch; int y_rows; long long y_cols;
+  int M;                       /* valid rows of X (= x_rows)                               */
+  int C, KH, KW;               /* output index mapping; KH*KW*C gradient columns per row   */
+  int tap_row0[CG_MAX_KH];
+  int tap_coloff[CG_MAX_KH];
+  int nkb;                     /* 32-wide k-blocks per slot segment                        */
+  long long x_slot_stride;     /* columns per slot in X                                    */
+  long long y_slot_stride;     /* columns per slot in Y                                    */
+  int group_mode;              /* CG_GROUP_SAMPLE: group g covers slots slot_lo+g + s*seg_stride, s<n_seg
+                                  CG_GROUP_SPLITK: group g covers slots [slot_lo+g*spg, min(.., slot_hi)) */
+  int n_groups;
+  int slot_lo, slot_hi, spg;
+  int n_seg, seg_stride;
+  int epi;
+  float* out;
+  long long out_group_stride;  /* CG_EPI_STORE: floats between groups                      */
+  int block_n;                 /* 0 = choose automatically; else multiple of 16, <= 128    */
+  int max_ctas;                /* 0 = one CTA per SM                                       */
+} cg_contract_desc;
+
+int cg_contract(const cg_contract_desc* d, cg_stream_t stream);
+
+/* Materialise Linear per-sample weight gradients (K = 1 outer products; upstream
+ * einsum("n...i,n...j->nij", B, A)): out[n][m][p] = X[m][slot0+n] * Y[p][slot0+n]. */
+int cg_outer_rows(const float* X, long long x_pitch, const float* Y, long long y_pitch, int M, int P,
+                  int slot0, int B, float* out, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small reductions around the contraction
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[i] = sum_j src[i*ld + j]^2 (accumulate!=0: +=).  Used for per-sample bias norms and as the
+ * first half of row_l2_norm. */
+int cg_row_sumsq(const float* src, long long rows, long long cols, long long ld, float* out,
+                 int accumulate, cg_stream_t stream);
+
+/* out[i] = a[i] * b[i]  (closed-form Linear norm ||b a^T||_F^2 = ||a||^2 ||b||^2). */
+int cg_vec_mul(const float* a, const float* b, float* out, long long n, cg_stream_t stream);
+
+/* Clip factors (replaces norm_clipper.calc_clipping_factors, reference train.py:324-328):
+ *   norm2 [n_params][n_slots] squared per-parameter norms.
+ *   per_layer == 0: total = sqrt(sum_k norm2[k][s]); factors[0][s] = min(1, C[0]/(total+1e-6));
+ *                   norms_out[0][s] = total
+ *   per_layer != 0: factors[k][s] = min(1, C[k]/(sqrt(norm2[k][s])+1e-6)); norms_out[k][s] = sqrt(..)
+ *   clip_lo..clip_hi: slots outside this range get factor 1 (unclipped non-private pass switch).
+ * C is a DEVICE array (so adaptive clipping never syncs the host). */
+int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C,
+                    int clip_lo, int clip_hi, float* factors, float* norms_out, cg_stream_t stream);
+
+/* dst[r][slot*slot_stride + q] = tf32(src[...] * factor[slot]) for slot in [slot_lo, slot_hi). */
+int cg_scale_slots(const float* src, float* dst, int rows, long long pitch, long long slot_stride,
+                   int slot_lo, int slot_hi, const float* factor, cg_stream_t stream);
+
+/* out[m][c][kh][kw] (+)= T[m][kh][kw*C + c]   (gradient-natural -> parameter layout) */
+int cg_permute_accum(const float* T, float* out, int M, int C, int KH, int KW, int accumulate,
+                     cg_stream_t stream);
+
+/* out[r] (+)= sum_slot factor[slot] * rows_in[slot*R + r], slot in [slot_lo, slot_hi)
+ * (clipped sum of per-sample bias gradients). */
+int cg_weighted_colsum(const float* rows_in, const float* factor, int slot_lo, int slot_hi, int R,
+                       float* out, int accumulate, cg_stream_t stream);
+
+/* stat over the slots of one pass of norms [n_rows][n_slots]: out[k] = mean or max of
+ * norms[k][slot_lo:slot_hi] times `scalar` (adaptive clipping, reference train.py:230-243,
+ * without the per-parameter .cpu().item() syncs).  stat: 0 = mean, 1 = max. */
+int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int slot_hi, int stat,
+                float scalar, float* out, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gaussian noise + finalisation of the step (replaces the patched optimizer.step():
+ * upstream privacy_engine.step / _generate_noise; reference train.py:484).
+ *   grad[i] = in[i] / in_div  +  (z_i * std) / noise_div          (each op rounded in fp32)
+ * z_i is bit-identical to the stream torch.normal(0, std, shape, generator=<CUDA generator with
+ * (seed, offset)>) would draw on this device: Philox4_32_10, curand_normal4, block 256,
+ * unroll 4, grid = min(SMs * maxThreadsPerSM/256, ceil(n/256)).  *offset_inc receives the amount
+ * the generator offset advances ( ((n-1)/(256*grid*4)+1)*4 ).  in_div / noise_div <= 0 disables
+ * the division.  `in` may be NULL (pure noise) or equal to `grad` (in-place add).
+ * ------------------------------------------------------------------------------------------- */
+int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, double std,
+                      double noise_div, unsigned long long seed, unsigned long long offset,
+                      unsigned long long* offset_inc, cg_stream_t stream);
+/* Same, but the standard deviation is std_mult * std_dev[0] with std_dev a DEVICE scalar (adaptive
+ * clipping thresholds / immediate sensitivities that never visit the host).  Always draws. */
+int cg_noise_finalize_dev(const float* in, float* grad, long long n, double in_div, double std_mult,
+                          const float* std_dev, double noise_div, unsigned long long seed,
+                          unsigned long long offset, unsigned long long* offset_inc, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-sample row norms (reference gradient_penalty.py:52-53, 60-61; immediate sensitivity,
+ * train.py:457/469) and per-sample L2 clipping (reference backprop_clip.py:18-22)
+ * ------------------------------------------------------------------------------------------- */
+/* norms[i] = ||src[i, :]||_2 */
+int cg_row_l2_norm(const float* src, long long rows, long long cols, float* norms, cg_stream_t stream);
+/* gin[i][j] = g[i][j] * (gout[i] / norms[i])   (backward of row_l2_norm; 0 where norms == 0) */
+int cg_row_l2_norm_bwd(const float* g, const float* norms, const float* gout, long long rows,
+                       long long cols, float* gin, cg_stream_t stream);
+/* out[0] = max_i v[i] */
+int cg_vec_max(const float* v, long long n, float* out, cg_stream_t stream);
+/* out[i,:] = norm_i > C ? C * (t[i,:] / norm_i) : t[i,:] ; norms_out optional */
+int cg_l2_clip(const float* t, long long rows, long long cols, float C, float* out, float* norms_out,
+               cg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSLGAN_B200_H */
