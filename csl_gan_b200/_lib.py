@@ -29,7 +29,7 @@ class UnfoldGeom(C.Structure):
 
 
 class UnfoldPlan(C.Structure):
-    _fields_ = [("n_rho", C.c_int), ("Hs", C.c_int), ("rows", C.c_int), ("slot_stride", C.c_int),
+    _fields_ = [("n_rho", C.c_int), ("Hs", C.c_int), ("Wop", C.c_int), ("rows", C.c_int), ("slot_stride", C.c_int),
                 ("tap_row0", C.c_int * CG_MAX_KH), ("tap_coloff", C.c_int * CG_MAX_KH),
                 ("rho", C.c_int * CG_MAX_KH), ("a_min", C.c_int)]
 
@@ -56,8 +56,8 @@ _PROTOS = {
     "cg_plan_unfold": (C.c_int, [C.POINTER(UnfoldGeom), C.POINTER(UnfoldPlan)]),
     "cg_stage_rows_t": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cg_stage_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong,
-                                C.c_int, C.c_void_p, C.c_void_p]),
+    "cg_stage_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "cg_stage_unfold": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(UnfoldGeom), C.POINTER(UnfoldPlan), C.c_float,
                                   C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cg_contract": (C.c_int, [C.POINTER(ContractDesc), C.c_void_p]),

@@ -105,6 +105,9 @@ int make_tmap(CUtensorMap* tm, const float* base, long long rows, long long cols
   return 0;
 }
 
+// fp32 reciprocal of a divisor, exactly as ATen's CUDA div-by-scalar computes it (1.0f / b); <= 0 disables
+float recip(double div) { return div > 0.0 ? 1.0f / static_cast<float>(div) : 0.0f; }
+
 int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 }  // namespace
@@ -151,9 +154,10 @@ int cg_plan_unfold(const cg_unfold_geom* g, cg_unfold_plan* plan) {
   plan->n_rho = n_rho;
   plan->a_min = a_min;
   plan->Hs = g->Ho + a_max - a_min;
+  plan->Wop = (g->Wo + 3) / 4 * 4;
   plan->rows = n_rho * g->KW * g->C;
-  plan->slot_stride = plan->Hs * g->Wo;
-  for (int kh = 0; kh < g->KH; ++kh) plan->tap_coloff[kh] = (a[kh] - a_min) * g->Wo;
+  plan->slot_stride = plan->Hs * plan->Wop;
+  for (int kh = 0; kh < g->KH; ++kh) plan->tap_coloff[kh] = (a[kh] - a_min) * plan->Wop;
   return 0;
 }
 
@@ -167,18 +171,19 @@ int cg_stage_rows_t(const float* src, int B, int R, float scale, float* dst, lon
   return 0;
 }
 
-int cg_stage_rows(const float* src, int B, int R, int Q, int Qpad, float scale, float* dst, long long dst_pitch,
-                  int slot0, float* rowsum, cg_stream_t stream) {
+int cg_stage_rows(const float* src, int B, int R, int Q, int Wo, int Wop, int Qpad, float scale, float* dst,
+                  long long dst_pitch, int slot0, float* rowsum, cg_stream_t stream) {
   if (B <= 0 || R <= 0) return 0;
-  if (Qpad < Q) return fail("Qpad (%d) < Q (%d)", Qpad, Q);
+  if (Wo <= 0 || Wop < Wo || Q % Wo) return fail("bad window row geometry Q=%d Wo=%d Wop=%d", Q, Wo, Wop);
+  if (Qpad < (Q / Wo) * Wop) return fail("Qpad (%d) too small for Q=%d Wo=%d Wop=%d", Qpad, Q, Wo, Wop);
   DevInfo d;
   if (dev_info(&d)) return 1;
   const long long nrows = static_cast<long long>(B) * R;
   const int block = 256;
   long long g = (nrows + 7) / 8;
   if (g > static_cast<long long>(d.sm) * 16) g = static_cast<long long>(d.sm) * 16;
-  cg::stage_rows_kernel<<<static_cast<int>(g), block, 0, S(stream)>>>(src, B, R, Q, Qpad, scale, dst, dst_pitch, slot0,
-                                                                      rowsum);
+  cg::stage_rows_kernel<<<static_cast<int>(g), block, 0, S(stream)>>>(src, B, R, Q, Wo, Wop, Qpad, scale, dst, dst_pitch,
+                                                                      slot0, rowsum);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -192,7 +197,7 @@ int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_u
   cg::UnfoldParams p;
   p.B = B; p.C = g->C; p.H = g->H; p.W = g->W; p.KW = g->KW;
   p.sh = g->sh; p.sw = g->sw; p.pw = g->pw; p.dw = g->dw;
-  p.Wo = g->Wo; p.Hs = plan->Hs; p.n_rho = plan->n_rho; p.a_min = plan->a_min;
+  p.Wo = g->Wo; p.Wop = plan->Wop; p.Hs = plan->Hs; p.n_rho = plan->n_rho; p.a_min = plan->a_min;
   for (int j = 0; j < CG_MAX_KH; ++j) p.rho[j] = plan->rho[j];
   p.scale = scale; p.dst_pitch = dst_pitch; p.slot0 = slot0;
   const long long total = static_cast<long long>(plan->rows) * B * plan->slot_stride;
@@ -355,7 +360,7 @@ static int noise_impl(const float* in, float* grad, long long n, double in_div, 
   if (!std_dev && !(std > 0.0)) {
     // upstream _generate_noise returns zeros when sigma*C == 0 and draws nothing from the generator
     if (in) {
-      cg::scale_copy_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(in, grad, n, static_cast<float>(in_div));
+      cg::scale_copy_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(in, grad, n, recip(in_div));
       CG_LAUNCH_CHECK();
     } else {
       CG_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n, S(stream)));
@@ -369,8 +374,7 @@ static int noise_impl(const float* in, float* grad, long long n, double in_div, 
   if (grid > cap) grid = cap;
   if (offset_inc) *offset_inc = ((static_cast<unsigned long long>(n) - 1) / (block * grid * 4) + 1) * 4;
   cg::noise_finalize_kernel<<<static_cast<unsigned int>(grid), block, 0, S(stream)>>>(
-      in, grad, n, static_cast<float>(in_div), static_cast<float>(std), static_cast<float>(noise_div), seed, offset,
-      std_dev);
+      in, grad, n, recip(in_div), static_cast<float>(std), recip(noise_div), seed, offset, std_dev);
   CG_LAUNCH_CHECK();
   return 0;
 }

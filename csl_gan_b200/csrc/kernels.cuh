@@ -70,8 +70,8 @@ __global__ void stage_rows_t_kernel(const float* __restrict__ src, int B, int R,
 // ------------------------------------------------------------------------------------------
 // stage_rows: src[B][R][Q] -> dst[r][(slot0+n)*Qpad + q], zero padded; one warp per (n, r) row
 // ------------------------------------------------------------------------------------------
-__global__ void stage_rows_kernel(const float* __restrict__ src, int B, int R, int Q, int Qpad, float scale,
-                                  float* __restrict__ dst, long long dst_pitch, int slot0,
+__global__ void stage_rows_kernel(const float* __restrict__ src, int B, int R, int Q, int Wo, int Wop, int Qpad,
+                                  float scale, float* __restrict__ dst, long long dst_pitch, int slot0,
                                   float* __restrict__ rowsum) {
   const long long nrows = static_cast<long long>(B) * R;
   const int lane = threadIdx.x & 31;
@@ -81,13 +81,20 @@ __global__ void stage_rows_kernel(const float* __restrict__ src, int B, int R, i
     const float* s = src + w * Q;
     float* d = dst + static_cast<long long>(r) * dst_pitch + static_cast<long long>(slot0 + n) * Qpad;
     float acc = 0.f;
-    for (int q = lane; q < Qpad; q += 32) {
+    for (int t = lane; t < Qpad; t += 32) {
       float v = 0.f;
-      if (q < Q) {
+      int q = t;
+      bool ok = t < Q;
+      if (Wop != Wo) {                      // padded window rows: t = oh*Wop + ow
+        const int oh = t / Wop, ow = t - oh * Wop;
+        q = oh * Wo + ow;
+        ok = ow < Wo && q < Q;
+      }
+      if (ok) {
         v = scale * s[q];
         acc += v;
       }
-      d[q] = round_tf32(v);
+      d[t] = round_tf32(v);
     }
     if (rowsum) {
       acc = warp_sum(acc);
@@ -98,12 +105,12 @@ __global__ void stage_rows_kernel(const float* __restrict__ src, int B, int R, i
 
 // ------------------------------------------------------------------------------------------
 // stage_unfold: src[B][C][H][W] -> kw-plane matrix
-//   dst[((j*KW + kw)*C + c)][ (slot0+n)*Hs*Wo + hs*Wo + ow ] = src[n][c][sh*(hs+a_min)+rho_j][ow*sw - pw + kw*dw]
+//   dst[((j*KW + kw)*C + c)][ (slot0+n)*Hs*Wop + hs*Wop + ow ] = src[n][c][sh*(hs+a_min)+rho_j][ow*sw - pw + kw*dw]
 // One thread per destination element; ow fastest so writes are coalesced and the strided reads
 // of neighbouring kw planes hit the same lines in L1/L2.
 // ------------------------------------------------------------------------------------------
 struct UnfoldParams {
-  int B, C, H, W, KW, sh, sw, pw, dw, Wo, Hs, n_rho, a_min;
+  int B, C, H, W, KW, sh, sw, pw, dw, Wo, Wop, Hs, n_rho, a_min;
   int rho[CG_MAX_KH];
   float scale;
   long long dst_pitch;
@@ -112,12 +119,12 @@ struct UnfoldParams {
 
 __global__ void stage_unfold_kernel(const float* __restrict__ src, const __grid_constant__ UnfoldParams p,
                                     float* __restrict__ dst) {
-  const long long per_row = static_cast<long long>(p.B) * p.Hs * p.Wo;
+  const long long per_row = static_cast<long long>(p.B) * p.Hs * p.Wop;
   const long long total = static_cast<long long>(p.n_rho) * p.KW * p.C * per_row;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int ow = static_cast<int>(i % p.Wo);
-    long long t = i / p.Wo;
+    const int ow = static_cast<int>(i % p.Wop);
+    long long t = i / p.Wop;
     const int hs = static_cast<int>(t % p.Hs);
     t /= p.Hs;
     const int n = static_cast<int>(t % p.B);
@@ -129,10 +136,10 @@ __global__ void stage_unfold_kernel(const float* __restrict__ src, const __grid_
     const int h = p.sh * (hs + p.a_min) + p.rho[j];
     const int w = ow * p.sw - p.pw + kw * p.dw;
     float v = 0.f;
-    if (h >= 0 && h < p.H && w >= 0 && w < p.W)
+    if (ow < p.Wo && h >= 0 && h < p.H && w >= 0 && w < p.W)
       v = p.scale * src[((static_cast<long long>(n) * p.C + c) * p.H + h) * p.W + w];
     const long long row = (static_cast<long long>(j) * p.KW + kw) * p.C + c;
-    dst[row * p.dst_pitch + (static_cast<long long>(p.slot0 + n) * p.Hs + hs) * p.Wo + ow] = round_tf32(v);
+    dst[row * p.dst_pitch + (static_cast<long long>(p.slot0 + n) * p.Hs + hs) * p.Wop + ow] = round_tf32(v);
   }
 }
 
@@ -307,7 +314,7 @@ __global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int
 // launched with exactly torch's geometry: block 256, grid = min(SMs*(maxThreads/256), ceil(n/256))
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4)
-noise_finalize_kernel(const float* in, float* grad, long long numel, float in_div, float stdv, float noise_div,
+noise_finalize_kernel(const float* in, float* grad, long long numel, float in_mul, float stdv, float noise_mul,
                       unsigned long long seed, unsigned long long offset, const float* __restrict__ std_dev) {
   if (std_dev) stdv = __fmul_rn(stdv, std_dev[0]);
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -323,11 +330,11 @@ noise_finalize_kernel(const float* in, float* grad, long long numel, float in_di
       const long long li = li0 + nthreads * ii;
       if (li < numel) {
         float nz = __fmul_rn(zz[ii], stdv);                 // torch.normal(0, std): rand * std + 0
-        if (noise_div > 0.f) nz = __fdiv_rn(nz, noise_div);  // noise /= batch_size
+        if (noise_mul > 0.f) nz = __fmul_rn(nz, noise_mul);  // noise /= batch_size  (torch CUDA: * 1/B)
         float g = 0.f;
         if (in) {
           g = in[li];
-          if (in_div > 0.f) g = __fdiv_rn(g, in_div);        // p.grad = summed_grad / batch_size
+          if (in_mul > 0.f) g = __fmul_rn(g, in_mul);        // p.grad = summed_grad / batch_size
           g = __fadd_rn(g, nz);                              // p.grad += noise
         } else {
           g = nz;
@@ -339,10 +346,10 @@ noise_finalize_kernel(const float* in, float* grad, long long numel, float in_di
 }
 
 // no-noise variant (sigma == 0 or C == 0): grad = in / in_div
-__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float div) {
+__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float mul) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = div > 0.f ? __fdiv_rn(in[i], div) : in[i];
+    out[i] = mul > 0.f ? __fmul_rn(in[i], mul) : in[i];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -103,7 +103,8 @@ class LayerPlan:
             self.Cn, self.KH, self.KW = Cn, kh, kw
             self.geom, self.plan = L.plan_unfold(Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo)
             self.Q = Ho * Wo
-            self.Qpad = _round_up(self.Q, KBLK)
+            self.Wo, self.Wop = Wo, self.plan.Wop
+            self.Qpad = _round_up(Ho * self.Wop, KBLK)
             self.x_slot_stride = self.Qpad
             self.y_slot_stride = self.plan.slot_stride
             self.tap_row0 = list(self.plan.tap_row0)
@@ -141,8 +142,8 @@ class LayerPlan:
             L.call("cg_stage_unfold", L.ptr(act), B, C.byref(self.geom), C.byref(self.plan), 1.0,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
         else:  # convT: the activation is the plain operand
-            L.call("cg_stage_rows", L.ptr(act), B, self.M, self.Q, self.Qpad, 1.0, L.ptr(self.X),
-                   self.X.stride(0), slot0, None, st)
+            L.call("cg_stage_rows", L.ptr(act), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, 1.0,
+                   L.ptr(self.X), self.X.stride(0), slot0, None, st)
 
     def capture_backprop(self, grad_out: torch.Tensor, pass_idx: int, scale: float):
         g = L.require_cuda_f32(grad_out.detach(), f"{self.name}: backprop")
@@ -154,15 +155,15 @@ class LayerPlan:
                    L.ptr(self.bias_rows), L.ptr(self.bsq), st)
         elif self.kind == "conv":
             # rowsum is indexed by absolute slot inside the kernel -> pass the buffer base
-            L.call("cg_stage_rows", L.ptr(g), B, self.M, self.Q, self.Qpad, scale, L.ptr(self.X),
-                   self.X.stride(0), slot0, L.ptr(self.bias_rows), st)
+            L.call("cg_stage_rows", L.ptr(g), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, scale,
+                   L.ptr(self.X), self.X.stride(0), slot0, L.ptr(self.bias_rows), st)
         else:
             L.call("cg_stage_unfold", L.ptr(g), B, C.byref(self.geom), C.byref(self.plan), scale,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
             if self.bias_rows is not None:
                 hw = g.shape[2] * g.shape[3]
-                L.call("cg_stage_rows", L.ptr(g), B, self.bias_len, hw, hw, scale, L.ptr(self._bias_scratch),
-                       self._bias_scratch.stride(0), 0, L.ptr(self.bias_rows[slot0:]), st)
+                L.call("cg_stage_rows", L.ptr(g), B, self.bias_len, hw, hw, hw, hw, scale,
+                       L.ptr(self._bias_scratch), self._bias_scratch.stride(0), 0, L.ptr(self.bias_rows[slot0:]), st)
 
     # ------------------------------------------------------------------ contraction launches
     def _desc(self, X: torch.Tensor) -> L.ContractDesc:

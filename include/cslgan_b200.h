@@ -23,7 +23,7 @@
  *             X[r][slot * x_slot_stride + q]   (Conv2d/Linear: backprops, r = out channel)
  *   Y operand "unfolded" side, staged as kw-planes so that every filter tap is a shifted
  *             window of a plain 2-D matrix (no im2col blow-up beyond KW * n_rho / (sh*sw)):
- *             Y[(j*KW + kw)*C + c][slot * y_slot_stride + hs*Wo + ow]
+ *             Y[(j*KW + kw)*C + c][slot * y_slot_stride + hs*Wop + ow]
  *   per-sample gradient of a layer  G_slot[m][c][kh][kw] = sum_q X[m][slot,q] * Y_tap[c][slot,q]
  */
 #ifndef CSLGAN_B200_H
@@ -59,10 +59,11 @@ typedef struct cg_unfold_geom {
 typedef struct cg_unfold_plan {
   int n_rho;                 /* distinct row residues (kh*dh - ph) mod sh               */
   int Hs;                    /* staged rows per plane = Ho + a_max - a_min              */
+  int Wop;                   /* Wo rounded up to 4: TMA box starts must be 16-byte aligned */
   int rows;                  /* staged matrix rows = n_rho * KW * C                     */
-  int slot_stride;           /* columns per slot = Hs * Wo                              */
+  int slot_stride;           /* columns per slot = Hs * Wop                             */
   int tap_row0[CG_MAX_KH];   /* first staged row of tap-group kh  (= j(kh) * KW * C)    */
-  int tap_coloff[CG_MAX_KH]; /* column offset of tap-group kh     (= (a(kh)-a_min)*Wo)  */
+  int tap_coloff[CG_MAX_KH]; /* column offset of tap-group kh     (= (a(kh)-a_min)*Wop) */
   int rho[CG_MAX_KH];        /* residue value of plane j                                */
   int a_min;
 } cg_unfold_plan;
@@ -82,12 +83,13 @@ int cg_plan_unfold(const cg_unfold_geom* g, cg_unfold_plan* plan);
 int cg_stage_rows_t(const float* src, int B, int R, float scale, float* dst, long long dst_pitch,
                     int slot0, float* copy_out, float* sumsq, cg_stream_t stream);
 
-/* src [B][R][Q] (conv backprops; ConvTranspose2d activations) ->
- *   dst[r][(slot0+n)*Qpad + q] = tf32(scale*src[n][r][q]), zero for Q <= q < Qpad.
- * Optional rowsum[(slot0+n)*R + r] = scale * sum_q src[n][r][q]  (per-sample bias gradients,
- *   upstream torch.sum(B, dim=2)). */
-int cg_stage_rows(const float* src, int B, int R, int Q, int Qpad, float scale, float* dst,
-                  long long dst_pitch, int slot0, float* rowsum, cg_stream_t stream);
+/* src [B][R][Q], Q = Ho*Wo (conv backprops; ConvTranspose2d activations) ->
+ *   dst[r][(slot0+n)*Qpad + oh*Wop + ow] = tf32(scale*src[n][r][oh*Wo + ow]), zero elsewhere
+ *   (Wop >= Wo is the padded window-row pitch of the matching unfolded operand; Wo = Wop = Q
+ *   stages a flat row).  Optional rowsum[(slot0+n)*R + r] = scale * sum_q src[n][r][q]
+ *   (per-sample bias gradients, upstream torch.sum(B, dim=2)). */
+int cg_stage_rows(const float* src, int B, int R, int Q, int Wo, int Wop, int Qpad, float scale,
+                  float* dst, long long dst_pitch, int slot0, float* rowsum, cg_stream_t stream);
 
 /* src [B][C][H][W] -> kw-plane matrix (see cg_unfold_plan), zero padding materialised. */
 int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_unfold_plan* plan,
@@ -182,7 +184,9 @@ int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int sl
 /* ---------------------------------------------------------------------------------------------
  * Gaussian noise + finalisation of the step (replaces the patched optimizer.step():
  * upstream privacy_engine.step / _generate_noise; reference train.py:484).
- *   grad[i] = in[i] / in_div  +  (z_i * std) / noise_div          (each op rounded in fp32)
+ *   grad[i] = in[i] * (1/in_div)  +  (z_i * std) * (1/noise_div)   (each op rounded in fp32;
+ *             torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal, and
+ *             bit-exactness is defined against that)
  * z_i is bit-identical to the stream torch.normal(0, std, shape, generator=<CUDA generator with
  * (seed, offset)>) would draw on this device: Philox4_32_10, curand_normal4, block 256,
  * unroll 4, grid = min(SMs * maxThreadsPerSM/256, ceil(n/256)).  *offset_inc receives the amount

@@ -1,0 +1,367 @@
+"""Engine-level parity on the GPU: csl_gan_b200.PrivacyEngine / ISPrivacyEngine (CUDA kernels through the
+C ABI) against the CPU oracle on identical seeded inputs, plus golden vectors from the reference."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import csl_gan_b200 as cg  # noqa: E402
+from csl_gan_b200 import discriminators as DD  # noqa: E402
+from oracle import dp_oracle as O  # noqa: E402
+
+DEV = "cuda"
+REL_TOL = 1e-3      # north_star: clipped summed gradients within 1e-3 relative tolerance (sigma = 0)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library_math():
+    """cuDNN / cuBLAS default to TF32 for the critic's own forward/backward on the GPU; the parity
+    target is the fp32 CPU oracle, so the library side runs in fp32 here (our kernels' TF32 operand
+    rounding is what the 1e-3 tolerance covers)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """normwise relative error with a small absolute floor (a reference that is exactly 0, e.g. a
+    bias whose clipped contributions cancel, must not turn rounding noise into an infinite ratio)."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / (b.norm() + 1e-5 * max(1.0, b.numel() ** 0.5))).item()
+
+
+def make(name):
+    torch.manual_seed(42)
+    if name == "mnist":
+        D = DD.MNISTVanillaD(n_classes=10, conditional_arch="ACGAN", aux_loss_type="cross_entropy")
+        shape, ncls, lo = (1, 28, 28), 10, 0.0
+    elif name == "mnist_uncond":
+        D = DD.MNISTVanillaD(n_classes=0)
+        shape, ncls, lo = (1, 28, 28), 0, 0.0
+    elif name == "mnist_dcrn":
+        D = DD.MNIST_DCRN_D(n_classes=0)
+        shape, ncls, lo = (1, 28, 28), 0, 0.0
+    elif name == "d64":
+        D = DD.CelebA_DCRN_D64(n_classes=0)
+        shape, ncls, lo = (3, 64, 64), 0, -1.0
+    elif name == "d48":
+        D = DD.CelebA_DCRN_D48(n_classes=0)
+        shape, ncls, lo = (3, 48, 48), 0, -1.0
+    else:
+        raise KeyError(name)
+    return D, shape, ncls, lo
+
+
+def batch(shape, ncls, lo, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    real = torch.rand((B,) + shape, generator=g) * (1 - lo) + lo
+    # a fake batch from a visibly different distribution so fake/real gradients do not cancel
+    fake = (torch.rand((B,) + shape, generator=g) * (1 - lo) + lo) * 0.5 + 0.25 * torch.randn((B,) + shape, generator=g)
+    y = torch.randint(0, ncls, (B,), generator=g) if ncls > 1 else None
+    return real, fake, y
+
+
+def d_loss(D, real, fake, y):
+    """train.py:382-384: fake pass first, then real pass; loss = real + fake (+ aux terms)."""
+    of, af = D(fake, y)
+    orr, ar = D(real, y)
+    loss = D.real_loss(orr) + D.fake_loss(of)
+    if ar is not None:
+        loss = loss + D.aux_loss(ar, y) + D.aux_loss(af, y, fake=True)
+    return loss
+
+
+def run_oracle(D, real, fake, y, B, C, sigma=0.0):
+    eng = O.OracleGCEngine(D, batch_size=B, noise_multiplier=sigma, max_grad_norm=C,
+                           accum_passes=False, num_private_passes=1)
+    eng.disable_hooks()
+    eng.enable_hooks()
+    d_loss(D, real, fake, y).backward()
+    eng.disable_hooks()
+    norms = eng.sample_norms()
+    factors = eng.clipping_factors(norms)
+    per_param_norms = O.calc_sample_norms(eng.grad_samples(), flat=False)
+    clipped = [c.clone() for c in eng.clip()]
+    eng.accum_grads_across_passes()
+    eng.accumulate_batch()
+    summed = [p.summed_grad.clone() for p in eng.params()]
+    eng.step_grads(None)
+    grads = [p.grad.clone() for p in eng.params()]
+    eng.remove()
+    return dict(norms=norms, factors=factors, per_param_norms=per_param_norms, clipped=clipped, summed=summed, grads=grads)
+
+
+def run_cuda(Dg, real, fake, y, B, C, sigma=0.0, seed=7):
+    opt = torch.optim.Adam(Dg.parameters(), lr=0.0)
+    eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=60000, noise_multiplier=sigma, max_grad_norm=C,
+                           accum_passes=False, num_private_passes=1, auto_clip_and_accum_on_step=False)
+    eng.disable_hooks()
+    eng.attach(opt)
+    eng._set_seed(seed)
+    for p in Dg.parameters():
+        p.grad = None
+    eng.enable_hooks()
+    yg = None if y is None else y.to(DEV)
+    d_loss(Dg, real.to(DEV), fake.to(DEV), yg).backward()
+    eng.expose_grad_sample_attrs()
+    assert next(iter(Dg.parameters())).grad_sample.size(1) == B          # train.py:388
+    eng.disable_hooks()
+    all_norms = cg.calc_sample_norms(named_params=eng.clipper._named_grad_samples(),
+                                     flat=not eng.clipper.norm_clipper.is_per_layer)          # train.py:311-314
+    per_param = eng.per_sample_norms().clone()
+    it = iter(eng.clipper.norm_clipper.calc_clipping_factors(all_norms))                      # train.py:324
+    factors = [next(it).clone() for _ in range(len(all_norms))]
+    eng.clip()
+    eng.accum_grads_across_passes()
+    eng.accumulate_batch()
+    summed = [p.summed_grad.clone() for p in Dg.parameters()]
+    opt.step()
+    grads = [p.grad.clone() for p in Dg.parameters()]
+    torch.cuda.synchronize()
+    return dict(norms=[n.clone() for n in all_norms], factors=factors, per_param_norms=per_param, summed=summed,
+                grads=grads, engine=eng)
+
+
+CASES = [
+    # model, B, C (float -> flat, list -> per layer), note
+    ("mnist", 600, 4.0),                   # BASELINE config 1: everything clips at random init
+    ("mnist", 64, "median"),               # both branches of min(1, C/n)
+    ("mnist", 37, [3.0, 0.2, 0.5, 0.2, 1.0, 0.5]),   # ragged batch, per-layer
+    ("mnist_uncond", 50, 2.0),
+    ("mnist_dcrn", 9, "median"),           # conv, Q=196 / 49 (ragged k tails), odd batch
+    ("d64", 6, [1000, 200, 1000, 100, 1000, 100, 1000, 5, 2500]),   # reference CelebA per-layer defaults: nothing clips
+    ("d64", 6, "median"),
+    ("d64", 5, "median-pl"),
+    ("d48", 3, "median"),
+]
+
+
+@pytest.mark.parametrize("name,B,C", CASES)
+def test_gc_step_matches_oracle(name, B, C):
+    D, shape, ncls, lo = make(name)
+    real, fake, y = batch(shape, ncls, lo, B, seed=B)
+    Dg = copy.deepcopy(D).to(DEV)
+    if isinstance(C, str):
+        probe = run_oracle(copy.deepcopy(D), real, fake, y, B, 1e9)
+        if C == "median":
+            C = float(probe["norms"][0].median())
+        else:
+            C = [float(n.median()) for n in probe["per_param_norms"]]
+    ref = run_oracle(D, real, fake, y, B, C)
+    got = run_cuda(Dg, real, fake, y, B, C)
+    # norms [n_passes, B] (flat: one item; per-layer: one per parameter)
+    assert len(got["norms"]) == len(ref["norms"])
+    for a, b in zip(got["norms"], ref["norms"]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+    for k, b in enumerate(ref["per_param_norms"]):
+        np.testing.assert_allclose(got["per_param_norms"][k].cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+    for a, b in zip(got["factors"], ref["factors"]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+    if not isinstance(C, list) and name != "d64":
+        f = ref["factors"][0]
+        assert (f < 0.999).any(), "test must exercise the clipped branch"
+    for k, (a, b) in enumerate(zip(got["summed"], ref["summed"])):
+        # the fake and real sums can cancel exactly (e.g. a bias whose every sample is clipped to +-C_k):
+        # allow 1e-5 of the per-pass magnitudes on top of the 1e-3 relative tolerance
+        floor = 1e-5 * sum(c.double().norm().item() for c in ref["clipped"][k])
+        err = (a.cpu().double() - b.double()).norm().item()
+        assert err <= REL_TOL * b.double().norm().item() + floor, (k, err, b.norm().item())
+        assert rel(got["grads"][k], ref["grads"][k]) < REL_TOL or err / B <= floor / B
+
+
+def test_lazy_grad_sample_view_and_materialize():
+    D, shape, ncls, lo = make("mnist_dcrn")
+    B = 5
+    real, fake, y = batch(shape, ncls, lo, B, seed=3)
+    ref_eng = O.OracleGCEngine(D, batch_size=B, noise_multiplier=0.0, max_grad_norm=1.0)
+    d_loss(D, real, fake, y).backward()
+    ref_gs = ref_eng.grad_samples()
+    Dg = copy.deepcopy(D).to(DEV)
+    for p in Dg.parameters():
+        p.grad = None
+    eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=1000, noise_multiplier=0.0, max_grad_norm=1.0,
+                           auto_clip_and_accum_on_step=False)
+    d_loss(Dg, real.to(DEV), fake.to(DEV), None).backward()
+    eng.expose_grad_sample_attrs()
+    for k, p in enumerate(Dg.parameters()):
+        gn = p.grad_sample[0].view(B, -1).norm(2, dim=1)                 # train.py:233 access pattern
+        np.testing.assert_allclose(gn.cpu().numpy(), ref_gs[k][0].reshape(B, -1).norm(2, dim=1).numpy(), rtol=1e-3, atol=1e-7)
+        full = p.grad_sample.materialize()
+        assert tuple(full.shape) == tuple(ref_gs[k].shape)
+        assert rel(full, ref_gs[k]) < REL_TOL
+    th = eng.adaptive_thresholds("mean", 1.5, pass_idx=0)                 # train.py:230-241 without host syncs
+    ref_th = torch.stack([g[0].reshape(B, -1).norm(2, dim=1).mean() * 1.5 for g in ref_gs])
+    np.testing.assert_allclose(th.cpu().numpy(), ref_th.numpy(), rtol=1e-3)
+    eng.set_max_grad_norm(th)                                             # device thresholds, per layer
+    assert eng.is_per_layer
+    eng.clip()
+    eng.accumulate_batch()
+    ref_eng.remove()
+
+
+def test_noise_step_bit_exact_vs_torch_generator():
+    """sigma > 0: the noise the engine adds equals what the upstream op sequence draws from a CUDA
+    torch.Generator seeded the same way (one torch.normal per parameter tensor, in order)."""
+    D, shape, ncls, lo = make("mnist")
+    B, C, sigma, seed = 64, 4.0, 10.0, 4242
+    real, fake, y = batch(shape, ncls, lo, B, seed=1)
+    Dg = copy.deepcopy(D).to(DEV)
+    got = run_cuda(Dg, real, fake, y, B, C, sigma=sigma, seed=seed)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(seed)
+    for s, g in zip(got["summed"], got["grads"]):
+        noise = torch.normal(0.0, sigma * C, s.shape, device=DEV, generator=gen)
+        ref = s / B
+        noise /= B
+        ref += noise
+        assert torch.equal(g, ref)
+    # the stream continues where it left off on the next step (offset bookkeeping)
+    eng = got["engine"]
+    off = int.from_bytes(bytes(gen.get_state()[8:16].tolist()), "little")
+    assert eng._philox_offset == off
+    # per-layer thresholds use sigma * C_k
+    Dg2 = copy.deepcopy(D).to(DEV)
+    Cs = [3.0, 0.2, 0.5, 0.2, 1.0, 0.5]
+    got2 = run_cuda(Dg2, real, fake, y, B, Cs, sigma=sigma, seed=seed)
+    gen.manual_seed(seed)
+    for s, g, c in zip(got2["summed"], got2["grads"], Cs):
+        noise = torch.normal(0.0, sigma * c, s.shape, device=DEV, generator=gen)
+        ref = s / B
+        noise /= B
+        ref += noise
+        assert torch.equal(g, ref)
+
+
+def test_split_clip_fake_switch_and_penalty_on_summed_grad():
+    """U1 switch: fake pass unclipped; and train.py:431 mutates p.summed_grad between accumulate_batch and step."""
+    D, shape, ncls, lo = make("mnist_uncond")
+    B = 24
+    real, fake, y = batch(shape, ncls, lo, B, seed=9)
+    ref_eng = O.OracleGCEngine(D, batch_size=B, noise_multiplier=0.0, max_grad_norm=1.0, split_clip_fake=False)
+    d_loss(D, real, fake, y).backward()
+    ref_eng.clip(); ref_eng.accum_grads_across_passes(); ref_eng.accumulate_batch()
+    Dg = copy.deepcopy(D).to(DEV)
+    for p in Dg.parameters():
+        p.grad = None
+    opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+    eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=1000, noise_multiplier=0.0, max_grad_norm=1.0,
+                           num_private_passes=1, split_clip_fake=False, auto_clip_and_accum_on_step=False)
+    eng.attach(opt)
+    d_loss(Dg, real.to(DEV), fake.to(DEV), None).backward()
+    eng.disable_hooks()
+    eng.clip(); eng.accum_grads_across_passes(); eng.accumulate_batch()
+    for p, q in zip(Dg.parameters(), ref_eng.params()):
+        assert rel(p.summed_grad, q.summed_grad) < REL_TOL
+        p.summed_grad += torch.ones_like(p) * B          # what train.py:431 does with the penalty gradient
+    opt.step()
+    for p, q in zip(Dg.parameters(), ref_eng.params()):
+        assert rel(p.grad, q.summed_grad / B + 1.0) < REL_TOL
+    ref_eng.remove()
+    with pytest.raises(ValueError):
+        eng.step()                                         # nothing accumulated
+
+
+@pytest.mark.parametrize("name,B,per_param", [("mnist", 64, False), ("mnist", 32, True), ("mnist_dcrn", 6, True),
+                                              ("d64", 4, False)])
+def test_immediate_sensitivity_matches_oracle(name, B, per_param):
+    D, shape, ncls, lo = make(name)
+    real, fake, y = batch(shape, ncls, lo, B, seed=11)
+    x = real.clone().requires_grad_(True)
+    of, af = D(fake, y)
+    orr, ar = D(x, y)
+    loss = D.real_loss(orr) + D.fake_loss(of)
+    if ar is not None:
+        loss = loss + D.aux_loss(ar, y) + D.aux_loss(af, y, fake=True)
+    g_ref, s_ref, ps_ref = O.immediate_sensitivity(list(D.parameters()), loss, x, per_param=per_param)
+
+    Dg = copy.deepcopy(D).to(DEV)
+    opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+    eng = cg.ISPrivacyEngine(Dg, batch_size=B, sample_size=60000, noise_multiplier=0.0, per_param=per_param)
+    eng.attach(opt)
+    eng._set_seed(5)
+    xg = real.to(DEV).requires_grad_(True)
+    yg = None if y is None else y.to(DEV)
+    of, af = Dg(fake.to(DEV), yg)
+    orr, ar = Dg(xg, yg)
+    lg = Dg.real_loss(orr) + Dg.fake_loss(of)
+    if ar is not None:
+        lg = lg + Dg.aux_loss(ar, yg) + Dg.aux_loss(af, yg, fake=True)
+    eng.backward(lg, xg)
+    for p, gr in zip(Dg.parameters(), g_ref):
+        assert rel(p.grad, gr) < 1e-4
+    s = eng.batch_sensitivity
+    if per_param:
+        np.testing.assert_allclose(np.asarray(s), np.asarray(s_ref), rtol=2e-3, atol=1e-7)
+    else:
+        assert abs(s - s_ref) / s_ref < 2e-3
+    np.testing.assert_allclose(eng._per_sample_sens.cpu().numpy(), ps_ref.numpy(), rtol=5e-3, atol=1e-6)
+    before = [p.grad.clone() for p in Dg.parameters()]
+    opt.step()                                            # sigma = 0: grads unchanged
+    for p, b in zip(Dg.parameters(), before):
+        assert torch.equal(p.grad, b)
+
+
+def test_immediate_sensitivity_noise_bit_exact():
+    D, shape, ncls, lo = make("mnist_uncond")
+    B, sigma, seed = 16, 10.0, 99
+    real, fake, y = batch(shape, ncls, lo, B, seed=2)
+    Dg = copy.deepcopy(D).to(DEV)
+    opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+    eng = cg.ISPrivacyEngine(Dg, batch_size=B, sample_size=60000, noise_multiplier=sigma, per_param=False)
+    eng.attach(opt)
+    eng._set_seed(seed)
+    xg = real.to(DEV).requires_grad_(True)
+    loss = Dg.real_loss(Dg(xg)[0]) + Dg.fake_loss(Dg(fake.to(DEV))[0])
+    eng.backward(loss, xg)
+    s = torch.tensor(eng.batch_sensitivity, dtype=torch.float32, device=DEV)
+    before = [p.grad.clone() for p in Dg.parameters()]
+    opt.step()
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(seed)
+    std = torch.tensor(sigma, dtype=torch.float32, device=DEV) * s          # fp32 product, like the kernel
+    for p, b in zip(Dg.parameters(), before):
+        z = torch.normal(0.0, 1.0, p.shape, device=DEV, generator=gen)
+        assert torch.equal(p.grad, b + z * std)
+
+
+@pytest.mark.parametrize("name", ["mnist_vanilla_acgan", "mnist_dcrn_acgan", "celeba_d64_uncond", "celeba_d48_uncond"])
+def test_gradient_penalty_matches_reference_golden(golden_dir, name):
+    """calc_lipschitz_penalty_WRT / calc_WGAN_GP_penalty with the CUDA row-norm vs outputs of the
+    reference's gradient_penalty.py (generated by oracle/gen_golden.py)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ctor = {"mnist_vanilla_acgan": lambda: DD.MNISTVanillaD(n_classes=10, conditional_arch="ACGAN", aux_loss_type="cross_entropy"),
+            "mnist_dcrn_acgan": lambda: DD.MNIST_DCRN_D(n_classes=10, conditional_arch="ACGAN", aux_loss_type="wasserstein"),
+            "celeba_d64_uncond": lambda: DD.CelebA_DCRN_D64(n_classes=0),
+            "celeba_d48_uncond": lambda: DD.CelebA_DCRN_D48(n_classes=0)}[name]
+    torch.manual_seed(42)
+    D = ctor().to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    y = torch.from_numpy(g["y"]).to(DEV) if g["y"].size else None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pen = cg.calc_lipschitz_penalty_WRT(D, x, y, per_sample=True, one_sided=False, aux_penalty=True)
+    np.testing.assert_allclose(pen.detach().cpu().numpy(), g["lip_pen_two_sided_aux"], rtol=2e-3, atol=1e-5)
+    pen1 = cg.calc_lipschitz_penalty_WRT(D, x, y, per_sample=True, one_sided=True, aux_penalty=False)
+    np.testing.assert_allclose(pen1.detach().cpu().numpy(), g["lip_pen_one_sided_noaux"], rtol=2e-3, atol=1e-5)
+    torch.manual_seed(777)
+    alpha = torch.rand(x.shape[0], 1)                                      # CPU draw, like gradient_penalty.py:33
+    gp = cg.calc_penalty(D, ["WGAN-GP"], x, y, torch.from_numpy(g["fake"]).to(DEV), y, aux_penalty=True, alpha=alpha)
+    np.testing.assert_allclose(gp.detach().cpu().numpy(), g["wgan_gp_seed777"], rtol=2e-3, atol=1e-5)
+    grads = torch.autograd.grad(gp, list(D.parameters()), allow_unused=True)
+    got = np.array([0.0 if t is None else t.double().norm().item() for t in grads])
+    np.testing.assert_allclose(got, g["wgan_gp_grad_norms"], rtol=5e-3, atol=1e-6)
+
+
+def test_engine_rejects_cpu_module_and_batchnorm():
+    D, *_ = make("mnist_uncond")
+    with pytest.raises(cg.CslGanCudaError):
+        cg.PrivacyEngine(D, batch_size=4, sample_size=100, noise_multiplier=1.0, max_grad_norm=1.0)
+    bad = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4)).to(DEV)
+    with pytest.raises(NotImplementedError):
+        cg.PrivacyEngine(bad, batch_size=4, sample_size=100, noise_multiplier=1.0, max_grad_norm=1.0)
