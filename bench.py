@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- per-sample clipped gradients / second for one DP discriminator step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--batch B] [--impl reference]
+
+Metric (BASELINE.json): per-sample clipped grads/sec (DP D-step), plus the fraction of roofline.
+  value   B_private_total / t_dp : the DP machinery only, captured (activation, grad_output) tensors
+          already resident in HBM -> staging -> per-sample norms -> clip factors -> clipped sum ->
+          (allreduce) -> Philox noise -> p.grad.  2 passes (fake + real) are contracted per sample.
+  e2e     the same metric through the public API (DiscriminatorStep): pinned-host images -> H2D ->
+          D forward fake+real -> backward with capture hooks -> clip -> accumulate -> noise + Adam ->
+          D2H of the loss, everything inside the timed region.
+  roofline  the tcgen05 contraction kernel: algorithmic FLOPs (n_passes * B * F_psg, counted once even
+          though norms and the clipped sum each run the contraction) / its CUDA-event time per step,
+          against the TF32 matmul peak measured live the way MEASURED_PEAKS.json measures bf16.
+  cpu_baseline  the CPU oracle (restatement of the opacus-fork path, see oracle/dp_oracle.py) on all
+          host cores over a bounded sample of the same workload.
+`--impl reference` prints the CPU arm alone (the reference's arithmetic lives in an un-vendored
+dependency, so the oracle port is the only runnable statement of it: kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_PSG = {"d64": 324_419_584, "mnist": 206_080}            # sum_layers 2*O*P*Q per (sample, pass)
+CELEBA_CPL = [1000, 200, 1000, 100, 1000, 100, 1000, 5, 2500]   # reference options.py:80
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["celeba_d64_gc", "mnist_gc"], default="celeba_d64_gc")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch size (weak scaling)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / cpu baseline")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+def make_workload(name: str, B: int, device, seed: int = 0):
+    from csl_gan_b200 import discriminators as DD
+    torch.manual_seed(42)                                   # reference weights_seed default
+    g = torch.Generator().manual_seed(1000 + seed)
+    if name == "celeba_d64_gc":
+        D = DD.CelebA_DCRN_D64(n_classes=0)
+        real = torch.rand(B, 3, 64, 64, generator=g) * 2 - 1
+        fake = torch.tanh(torch.randn(B, 3, 64, 64, generator=g))
+        y = None
+        cfg = dict(C=CELEBA_CPL, sigma=0.5, sample_size=180000, fpsg=F_PSG["d64"])
+    else:
+        D = DD.MNISTVanillaD(n_classes=10, conditional_arch="ACGAN", aux_loss_type="cross_entropy")
+        real = torch.rand(B, 1, 28, 28, generator=g)
+        fake = torch.sigmoid(torch.randn(B, 1, 28, 28, generator=g))
+        y = torch.randint(0, 10, (B,), generator=g)
+        cfg = dict(C=4.0, sigma=10.0, sample_size=60000, fpsg=F_PSG["mnist"])
+    return D.to(device), real, fake, y, cfg
+
+
+def d_loss(D, real, fake, y):
+    of, af = D(fake, y)
+    orr, ar = D(real, y)
+    loss = D.real_loss(orr) + D.fake_loss(of)
+    if ar is not None:
+        loss = loss + D.aux_loss(ar, y) + D.aux_loss(af, y, fake=True)
+    return loss
+
+
+def grab_captures(D, real, fake, y):
+    """Run fake+real forward/backward once with plain hooks and keep every layer's (input, grad_output)."""
+    from csl_gan_b200.privacy_engine import SUPPORTED_LAYERS
+    passes, count, handles = [], {}, []
+
+    def mk(name):
+        def fwd(layer, inp, out):
+            k = count.get(name, 0)
+            count[name] = k + 1
+            while len(passes) <= k:
+                passes.append({})
+            passes[k][name] = [inp[0].detach().clone(), None]
+            out.register_hook(lambda gr, k=k: passes[k][name].__setitem__(1, gr.detach().clone()))
+        return fwd
+    for name, m in D.named_modules():
+        if isinstance(m, SUPPORTED_LAYERS):
+            handles.append(m.register_forward_hook(mk(name)))
+    d_loss(D, real, fake, y).backward()
+    for h in handles:
+        h.remove()
+    for p in D.parameters():
+        p.grad = None
+    return [{n: (a, g) for n, (a, g) in d.items()} for d in passes]
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def timed(fn, steps, warmup, dist_on):
+    """W warm-up calls, then exactly K calls between CUDA events; barrier + synchronize on both sides;
+    max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def measure_tf32_peak():
+    """TF32 matmul peak, measured the way MEASURED_PEAKS.json measures bf16 (8192^3, best of 10)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device="cuda")
+    b = torch.randn(8192, 8192, device="cuda")
+    best = 1e9
+    for _ in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_step_rate(workload: str, B: int, steps: int, warmup: int):
+    """Full DP D-step of the CPU oracle (fwd fake+real, backward with grad-sample hooks, norms, clip,
+    weighted sum, accumulate, noise) on all host cores; returns (samples/s, ms/step, cores)."""
+    from oracle import dp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    D, real, fake, y, cfg = make_workload(workload, B, "cpu")
+    gen = torch.Generator().manual_seed(1)
+    eng = O.OracleGCEngine(D, batch_size=B, noise_multiplier=cfg["sigma"], max_grad_norm=cfg["C"],
+                           accum_passes=False, num_private_passes=1)
+
+    def step():
+        for p in D.parameters():
+            p.grad = None
+        eng.enable_hooks()
+        d_loss(D, real, fake, y).backward()
+        eng.disable_hooks()
+        eng.clip()
+        eng.accum_grads_across_passes()
+        eng.accumulate_batch()
+        eng.step_grads(lambda k, std, shape: torch.normal(0.0, std, shape, generator=gen))
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    eng.remove()
+    return B / dt, dt * 1e3, cores
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """CPU arm: the oracle port on the host cores, bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    B_full = args.batch or (512 if args.workload == "celeba_d64_gc" else 600)
+    B = min(B_full, 64 if args.workload == "celeba_d64_gc" else 600)
+    steps = max(1, min(args.steps, 5 if args.workload == "celeba_d64_gc" else 20))
+    warm = max(1, min(args.warmup, 1 if args.workload == "celeba_d64_gc" else 3))
+    rate, ms, cores = cpu_step_rate(args.workload, B, steps, warm)
+    sample = f"full DP D-step of the oracle port, B={B} of {B_full}, {steps} timed steps after {warm} warm-up"
+    line = {
+        "impl": "reference", "metric": "per-sample clipped grads/sec (DP D-step)", "value": rate,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "per_gpu_batch": B_full, "n_passes": 2, "device": "cpu"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the DP hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    import csl_gan_b200 as cg
+    from csl_gan_b200 import _lib as L
+    from csl_gan_b200.dstep import DiscriminatorStep
+    from csl_gan_b200 import options as OPT
+
+    wl = args.workload
+    B = args.batch or (512 if wl == "celeba_d64_gc" else 600)
+    D, real_h, fake_h, y_h, cfg = make_workload(wl, B, dev, seed=rank)
+    real_pin, fake_pin = real_h.pin_memory(), fake_h.pin_memory()
+    y_dev = None if y_h is None else y_h.to(dev)
+    opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9) if wl == "celeba_d64_gc" else (0.9, 0.999))
+    eng = cg.PrivacyEngine(D, batch_size=B, sample_size=cfg["sample_size"], noise_multiplier=cfg["sigma"],
+                           max_grad_norm=cfg["C"], accum_passes=False, num_private_passes=1,
+                           auto_clip_and_accum_on_step=False, data_parallel=dist_on)
+    eng.disable_hooks()
+    eng.attach(opt_d)
+    eng._set_seed(1234)
+
+    # ---- value: DP machinery with captured tensors resident in HBM ---------------------------------
+    caps = grab_captures(D, real_h.to(dev), fake_h.to(dev), y_dev)
+
+    def dp_only():
+        eng.ingest_captures(caps)
+        eng.clip()
+        eng.accum_grads_across_passes()
+        eng.accumulate_batch()
+        eng.step()
+
+    launches0 = L.launch_count
+    with ClockSampler(local) as clk:
+        ms_dp = timed(dp_only, args.steps, args.warmup, dist_on)
+    launches = (L.launch_count - launches0) // (args.steps + args.warmup)      # ABI launch calls per step
+    t_dp = ms_dp / args.steps
+    value = B * world / (t_dp * 1e-3)
+
+    # ---- kernel attribution: CUDA events around every ABI call, one extra pass of K steps -----------
+    L.set_profile(True)
+    for _ in range(args.steps):
+        dp_only()
+    torch.cuda.synchronize()
+    prof = L.profile_summary()
+    L.set_profile(False)
+    per_step = {k: (ms / args.steps, n // args.steps) for k, (ms, n) in prof.items()}
+    t_contract = per_step.get("cg_contract", (0.0, 0))[0]
+    flops_step = 2 * B * cfg["fpsg"]
+
+    # ---- e2e: public API, host buffers, H2D/D2H inside the timed region -----------------------------
+    argv = (["CelebA", "-dpm", "gc", "-gcm", "constant-pl", "--penalty"] if wl == "celeba_d64_gc"
+            else ["MNIST", "-dpm", "gc", "--conditional", "--sigma", "10"])
+    o = OPT.parse(argv + ["-bs", str(B)])
+    o.penalty = []
+    stepper = DiscriminatorStep(o, D, opt_d, eng)
+
+    def e2e_step():
+        r = real_pin.to(dev, non_blocking=True)
+        f = fake_pin.to(dev, non_blocking=True)
+        res = stepper(r, y_dev, f, y_dev, use_dp=True)
+        return (res.d_real_loss + res.d_fake_loss).item()          # D2H read of the step's result
+
+    ms_e2e = timed(e2e_step, args.steps, args.warmup, dist_on)
+    e2e_value = B * world / (ms_e2e / args.steps * 1e-3)
+    h2d = real_pin.numel() * 4 + fake_pin.numel() * 4
+    clocks = clk.summary()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf32_peak = measure_tf32_peak()
+        achieved = flops_step / (t_contract * 1e-3) / 1e12 if t_contract > 0 else None
+        roof = {"bound": "tensor", "kernel": "contract_kernel (tcgen05 kind::tf32)", "achieved": achieved,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None,
+                "peak_source": "TF32 torch.matmul 8192^3 best of 12, measured live (MEASURED_PEAKS.json has no TF32 figure)",
+                "bf16_peak_measured": peaks.get("bf16_tflops"),
+                "frac_of_bf16_peak": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
+                "algorithmic_flops_per_step": flops_step, "contract_ms_per_step": t_contract,
+                "contract_launches_per_step": per_step.get("cg_contract", (0, 0))[1],
+                "whole_dp_frac": flops_step / (t_dp * 1e-3) / 1e12 / tf32_peak,
+                "traffic": None}
+        line = {
+            "metric": "per-sample clipped grads/sec (DP D-step)", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dp,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands, f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "n_passes": 2,
+                       "contractions_per_step": 2 * B * world, "clipping": "per-layer" if isinstance(cfg["C"], list) else "flat",
+                       "sigma": cfg["sigma"], "parallelism": f"dp{world}",
+                       "l2": "staged operands per step exceed the 126 MB L2 (no flush needed)" if wl == "celeba_d64_gc"
+                             else "working set fits in L2; MNIST is launch-latency bound (SURVEY.md §8d)"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps,
+            "gpu_launches_per_step": launches,
+            "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][0])},
+            "roofline": roof,
+            "clocks": clocks,
+        }
+        if not args.no_extras and world == 1:
+            Bc = 64 if wl == "celeba_d64_gc" else 600
+            rate, ms, cores = cpu_step_rate(wl, Bc, 3, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"full DP D-step of the CPU oracle, B={Bc}, 3 timed steps after 1 warm-up "
+                                              f"({ms:.0f} ms/step); compare with e2e"}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

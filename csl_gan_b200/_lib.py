@@ -108,13 +108,40 @@ def load() -> C.CDLL:
     return lib
 
 
+_profile = None           # when a list: (name, start_event, end_event) per launching ABI call
+
+
+def set_profile(on: bool):
+    """Bracket every launching ABI call with CUDA events on the current stream (bench.py uses this
+    to attribute device time to kernels without a profiler attached)."""
+    global _profile
+    _profile = [] if on else None
+
+
+def profile_summary():
+    """{abi call: (total ms, launches)}; call after torch.cuda.synchronize()."""
+    out = {}
+    for name, e0, e1 in _profile or []:
+        ms, n = out.get(name, (0.0, 0))
+        out[name] = (ms + e0.elapsed_time(e1), n + 1)
+    return out
+
+
 def call(name: str, *args):
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    launching = name not in _NO_LAUNCH
+    if _profile is not None and launching:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _profile.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise CslGanCudaError(f"{name}: {lib.cg_last_error().decode(errors='replace')}")
-    if name not in _NO_LAUNCH:
+    if launching:
         launch_count += 1
 
 

@@ -1,0 +1,220 @@
+"""The differentially-private discriminator update, `train_D` re-authored around the CUDA engines.
+
+Mirrors reference train.py:360-500 (`train_D`), :95-138 (`setup_privacy_engine`), :204-245
+(`update_adaptive_clipping_params`), :247-249 (`update_sens_moving_avg`) and :310-338 (grad / IS
+logging), with the host synchronisations removed: adaptive thresholds, norm statistics and
+sensitivities stay on the device; logging values are returned as device tensors and only converted
+when the caller asks (`DStepResult.to_host()`).
+
+Out of scope here: the generator, datasets, MeanSampler, file logging.  The caller
+passes the fake batch (G's detached output) and, where a penalty or adaptive clipping needs it, a
+public batch.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import autograd, nn
+
+from .functional import calc_penalty
+from .is_engine import ISPrivacyEngine
+from .privacy_engine import PrivacyEngine, calc_sample_norms
+
+ALPHAS = [1 + x / 10.0 for x in range(1, 100)] + list(range(12, 400))      # reference train.py:99
+
+
+def setup_privacy_engine(opt, D: nn.Module, d_optimizer, **engine_kw):
+    """reference train.py:95-138."""
+    common = dict(batch_size=opt.batch_size, sample_size=opt.train_set_size, alphas=ALPHAS,
+                  noise_multiplier=opt.sigma)
+    if opt.dp_mode == "is":
+        eng = ISPrivacyEngine(
+            D, **common, per_param=opt.imm_sens_per_param,
+            scaling_vec=None if opt.imm_sens_scaling_mode == "standard" else opt.imm_sens_scaling_vec, **engine_kw)
+    elif opt.dp_mode == "gc":
+        n_params = len(list(D.parameters()))
+        if opt.clipping_param_per_layer is None:
+            opt.clipping_param_per_layer = [1 for _ in range(n_params)]
+        per_layer = opt.grad_clip_mode[-3:] == "-pl"
+        eng = PrivacyEngine(
+            D, **common, accum_passes=not opt.grad_clip_split,
+            num_private_passes=1 if opt.grad_clip_split else None, auto_clip_and_accum_on_step=False,
+            max_grad_norm=opt.clipping_param_per_layer if per_layer else opt.clipping_param, **engine_kw)
+        eng.disable_hooks()
+    else:
+        raise NotImplementedError(f"dp_mode {opt.dp_mode!r}")
+    eng.attach(d_optimizer)
+    eng._set_seed(opt.manual_seed)
+    return eng
+
+
+@dataclass
+class DStepResult:
+    d_real_loss: torch.Tensor
+    d_fake_loss: torch.Tensor
+    d_real: torch.Tensor
+    d_fake: torch.Tensor
+    penalty: Optional[torch.Tensor] = None
+    d_real_aux_loss: Optional[torch.Tensor] = None
+    d_real_aux: Optional[torch.Tensor] = None
+    stats: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+    def to_host(self) -> Dict[str, object]:
+        """One synchronisation for everything the reference logs per step (train.py:487-500)."""
+        out = {"D Real Loss": self.d_real_loss.item(), "D Fake Loss": self.d_fake_loss.item(),
+               "D Real Acc": 100 * float((self.d_real > 0).float().mean()),
+               "D Fake Acc": 100 * float((self.d_fake < 0).float().mean())}
+        out["D Adv Loss"] = out["D Real Loss"] + out["D Fake Loss"]
+        if self.penalty is not None:
+            out["D Penalty"] = float(self.penalty)
+        if self.d_real_aux_loss is not None:
+            out["D Real Aux Loss"] = float(self.d_real_aux_loss)
+        for k, v in self.stats.items():
+            out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v
+        return out
+
+
+class DiscriminatorStep:
+    def __init__(self, opt, D: nn.Module, d_optimizer, privacy_engine=None,
+                 public_batch: Optional[Callable[[int, Optional[torch.Tensor]], Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None,
+                 collect_stats: bool = False):
+        self.opt, self.D, self.opt_d, self.engine = opt, D, d_optimizer, privacy_engine
+        self.public_batch = public_batch
+        self.collect_stats = collect_stats
+
+    # ------------------------------------------------------------------ losses (train.py:342-358)
+    def _fake_loss(self, fake_img, y):
+        opt, D = self.opt, self.D
+        d_fake, d_fake_aux = D(fake_img, y, aux=opt.d_fake_aux_loss)
+        loss = D.fake_loss(d_fake, fake_img.device)
+        aux = D.aux_loss(d_fake_aux, y, fake_img.device, fake=True) if opt.use_aux_loss and opt.d_fake_aux_loss else 0
+        return d_fake, loss, aux
+
+    def _real_loss(self, img, labels):
+        opt, D = self.opt, self.D
+        d_real, d_real_aux = D(img, labels)
+        loss = D.real_loss(d_real, img.device)
+        aux = D.aux_loss(d_real_aux, labels, img.device, fake=False) if opt.use_aux_loss else 0
+        return d_real, d_real_aux, loss, aux
+
+    # ------------------------------------------------------------------ adaptive clipping (train.py:204-245)
+    def update_adaptive_clipping_params(self, fake_img, fake_y):
+        opt, eng = self.opt, self.engine
+        if self.public_batch is None:
+            raise RuntimeError("adaptive clipping needs a public batch source (mean samples or a public partition)")
+        for p in self.D.parameters():
+            p.grad = None
+        img, labels = self.public_batch(opt.batch_size, None)
+        loss = 0
+        if not opt.grad_clip_split:
+            _, fl, fa = self._fake_loss(fake_img, fake_y)
+            loss = fl + fa
+        _, _, rl, ra = self._real_loss(img, labels)
+        (loss + rl + ra).backward()
+        th = eng.adaptive_thresholds(opt.adaptive_stat, 1.0, pass_idx=0)          # device tensor, no sync
+        if opt.use_grad_clip_per_layer:
+            eng.set_max_grad_norm(th * opt.adaptive_scalar)
+        else:
+            eng.set_max_grad_norm(th.norm(2) * opt.adaptive_scalar)
+        self.opt_d.zero_grad()
+
+    def update_sens_moving_avg(self):
+        """train.py:247-249 (beta defaults to 0.9: the reference never defines opt.moving_avg_beta)."""
+        eng, beta = self.engine, self.opt.moving_avg_beta
+        norms = torch.stack([p.grad.reshape(-1).norm(2) for p in self.D.parameters()]).cpu().tolist()
+        eng.set_scaling_vec([v * beta + n * (1 - beta) for v, n in zip(eng.scaling_vec, norms)])
+
+    # ------------------------------------------------------------------ logging (train.py:310-338), device side
+    def _grad_stats(self) -> Dict[str, torch.Tensor]:
+        eng, opt = self.engine, self.opt
+        all_norms = calc_sample_norms(named_params=eng.clipper._named_grad_samples(),
+                                      flat=not eng.clipper.norm_clipper.is_per_layer)
+        ps = 1 if opt.grad_clip_split else 0
+        norms = torch.stack(all_norms)[:, min(ps, all_norms[0].shape[0] - 1)]
+        factors = iter(eng.clipper.norm_clipper.calc_clipping_factors(all_norms))
+        clipped = torch.stack([(next(factors)[min(ps, all_norms[0].shape[0] - 1)] < 0.999).float().mean()
+                               for _ in range(len(all_norms))])
+        return {"D Layer Grad Norm Means": norms.mean(dim=1), "D Layer Grad Norm Stds": norms.std(dim=1, unbiased=False),
+                "D Layer Grad Norm Maxes": norms.max(dim=1).values, "Grads Clipped": clipped}
+
+    # ------------------------------------------------------------------ the step (train.py:360-500)
+    def __call__(self, img, labels, fake_img, fake_y, use_dp: bool = True) -> DStepResult:
+        opt, D, eng = self.opt, self.D, self.engine
+        for p in D.parameters():
+            p.grad = None
+        batch_size = img.size(0)
+        use_gc = opt.dp_mode == "gc" and use_dp
+        use_is = opt.dp_mode == "is" and use_dp
+        fake_img = fake_img.detach()
+
+        if opt.per_sample_grad and use_dp:
+            eng.enable_hooks()
+        if use_is:
+            img = img.detach().requires_grad_(True)
+        if use_gc and opt.grad_clip_mode[:8] == "adaptive":
+            self.update_adaptive_clipping_params(fake_img, fake_y)
+
+        d_fake, d_fake_loss, d_fake_aux_loss = self._fake_loss(fake_img, fake_y)
+        d_real, d_real_aux, d_real_loss, d_real_aux_loss = self._real_loss(img, labels)
+        d_loss = d_real_loss + d_fake_loss + d_real_aux_loss + d_fake_aux_loss
+        res = DStepResult(d_real_loss.detach(), d_fake_loss.detach(), d_real.detach(), d_fake.detach())
+        if opt.use_aux_loss:
+            res.d_real_aux_loss, res.d_real_aux = d_real_aux_loss.detach(), d_real_aux.detach()
+
+        if opt.per_sample_grad and use_dp:
+            d_loss.backward()
+            eng.disable_hooks()
+        if use_gc:
+            if self.collect_stats:
+                with torch.no_grad():
+                    res.stats.update(self._grad_stats())
+            eng.clip()
+            if opt.grad_clip_split:
+                eng.accum_grads_across_passes()
+
+        has_penalty = len(opt.penalty) > 0
+        if has_penalty:
+            pen_real, pen_labels = img, labels
+            if opt.penalty_use_public_data and self.public_batch is not None:
+                pen_real, pen_labels = self.public_batch(batch_size, labels)
+            if use_dp and opt.per_sample_grad:
+                if not opt.penalty_use_public_data:
+                    raise NotImplementedError(
+                        "per-sample penalties on private data (-pupd False) leak memory in the reference "
+                        "(train.py:435-436) and are not reproduced; use public data / mean samples")
+                eng.accumulate_batch()
+                penalty = calc_penalty(D, opt.penalty, pen_real, pen_labels, fake_img, fake_y, device=img.device,
+                                       aux_penalty=opt.aux_penalty)
+                pgrad = autograd.grad(penalty, list(D.parameters()), allow_unused=True)
+                with torch.no_grad():
+                    for p, g in zip(D.parameters(), pgrad):
+                        if g is not None:
+                            p.summed_grad.add_(g, alpha=float(opt.batch_size))     # summed_grad is a sum (train.py:431)
+            else:
+                penalty = calc_penalty(D, opt.penalty, pen_real, pen_labels, fake_img, fake_y, device=img.device,
+                                       aux_penalty=opt.aux_penalty)
+                d_loss = d_loss + penalty
+                if use_is:
+                    eng.backward(d_loss, img)
+                    if opt.imm_sens_scaling_mode == "moving-avg-pl":
+                        self.update_sens_moving_avg()
+                else:
+                    d_loss.backward()
+            res.penalty = penalty.detach()
+        else:
+            if use_gc:
+                eng.accumulate_batch()
+            elif use_is:
+                eng.backward(d_loss, img)
+                if opt.imm_sens_scaling_mode == "moving-avg-pl":
+                    self.update_sens_moving_avg()
+            else:
+                d_loss.backward()
+        if use_is and self.collect_stats:
+            res.stats["IS"] = eng._sens_dev.detach().clone()
+
+        self.opt_d.step()
+        return res

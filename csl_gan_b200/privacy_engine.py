@@ -326,6 +326,27 @@ class PrivacyEngine:
                 output.register_hook(grad_hook)
         return fwd_hook
 
+    def ingest_captures(self, passes: Sequence[Dict[str, Tuple[torch.Tensor, torch.Tensor]]]):
+        """Feed already-captured (activation, grad_output) pairs, one dict {layer name: (A, G)} per
+        pass in forward order, exactly as the hooks would have staged them.  This is the hot path with
+        its inputs resident in HBM (what bench.py times as t_dp) and a handy seam for tests."""
+        self._reset_capture()
+        by_name = {pl.name: pl for pl in self._plans}
+        for ps, layers in enumerate(passes):
+            for name, (act, gout) in layers.items():
+                plan = by_name[name]
+                B = act.shape[0]
+                if B > self.Bpad:
+                    self.Bpad = _round_up(B, 32)
+                    self._alloc_state()
+                self._pass_count[plan] = max(self._pass_count.get(plan, 0), ps + 1)
+                self._pass_B[ps] = B
+                self._cur_B = B
+                plan.capture_activation(act, ps, self.Bpad, self.max_passes)
+                if gout is not None:
+                    plan.capture_backprop(gout, ps, float(B) if self.loss_reduction == "mean" else 1.0)
+                    self._bp_seen.add((plan, ps))
+
     def _reset_capture(self):
         self._pass_count: Dict[LayerPlan, int] = {}
         self._pass_B: Dict[int, int] = {}
