@@ -200,8 +200,21 @@ int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_u
   p.Wo = g->Wo; p.Wop = plan->Wop; p.Hs = plan->Hs; p.n_rho = plan->n_rho; p.a_min = plan->a_min;
   for (int j = 0; j < CG_MAX_KH; ++j) p.rho[j] = plan->rho[j];
   p.scale = scale; p.dst_pitch = dst_pitch; p.slot0 = slot0;
-  const long long total = static_cast<long long>(plan->rows) * B * plan->slot_stride;
-  cg::stage_unfold_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(src, p, dst);
+  const long long hw = static_cast<long long>(g->H) * g->W;
+  if (hw <= 8192 && B <= 65535) {
+    // shared-memory path: each block reads `cpb` input planes once and emits all their kw-planes
+    int cpb = static_cast<int>(8192 / hw);
+    if (cpb > g->C) cpb = g->C;
+    if (cpb < 1) cpb = 1;
+    // keep enough blocks in flight: at least ~4 waves when the problem allows it
+    while (cpb > 1 && static_cast<long long>((g->C + cpb - 1) / cpb) * B < 4LL * d.sm) cpb = (cpb + 1) / 2;
+    dim3 grid((g->C + cpb - 1) / cpb, B);
+    const size_t smem = static_cast<size_t>(cpb) * hw * sizeof(float);
+    cg::stage_unfold_smem_kernel<<<grid, 256, smem, S(stream)>>>(src, p, dst, cpb);
+  } else {
+    const long long total = static_cast<long long>(plan->rows) * B * plan->slot_stride;
+    cg::stage_unfold_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(src, p, dst);
+  }
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -220,12 +233,22 @@ int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
   p.KWC = d->KW * d->C;
   int bn = d->block_n;
   if (bn <= 0) {
-    bn = cg::kMaxBN;
-    if (p.KWC < bn) bn = ((p.KWC + 15) / 16) * 16;
+    // widest tile that wastes the fewest padded columns: ceil(KWC / ceil(KWC/256)) rounded up to 16
+    const int parts = (p.KWC + cg::kMaxBN - 1) / cg::kMaxBN;
+    bn = (((p.KWC + parts - 1) / parts) + 15) / 16 * 16;
   }
-  if (bn % 16 || bn < 16 || bn > cg::kMaxBN) return fail("block_n must be a multiple of 16 in [16,128]");
+  if (bn % 16 || bn < 16 || bn > cg::kMaxBN) return fail("block_n must be a multiple of 16 in [16,256]");
   p.BN = bn;
   p.n_rb = (p.KWC + bn - 1) / bn;
+  // narrow layers: stack several filter-row taps along N so the X tile is fetched once for all of them
+  p.ks = 1;
+  if (p.n_rb == 1) {
+    p.ks = cg::kMaxBN / bn;
+    if (p.ks > d->KH) p.ks = d->KH;
+    if (p.ks < 1) p.ks = 1;
+  }
+  p.n_khg = (d->KH + p.ks - 1) / p.ks;
+  p.NT = p.ks * bn;
   p.C = d->C; p.KH = d->KH; p.KW = d->KW;
   for (int i = 0; i < CG_MAX_KH; ++i) { p.tap_row0[i] = d->tap_row0[i]; p.tap_coloff[i] = d->tap_coloff[i]; }
   p.nkb = d->nkb;
@@ -240,7 +263,7 @@ int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
   } else if (p.n_seg <= 0) {
     return fail("n_seg must be positive");
   }
-  p.n_items = static_cast<long long>(p.n_groups) * p.KH * p.n_rb * p.n_mtiles;
+  p.n_items = static_cast<long long>(p.n_groups) * p.n_khg * p.n_rb * p.n_mtiles;
 
   CUtensorMap tx, ty;
   if (make_tmap(&tx, d->X, d->x_rows, d->x_cols, d->x_pitch, cg::kBM)) return 1;
@@ -311,9 +334,18 @@ int cg_scale_slots(const float* src, float* dst, int rows, long long pitch, long
   if (rows <= 0 || slot_hi <= slot_lo) return 0;
   DevInfo d;
   if (dev_info(&d)) return 1;
-  const long long total = static_cast<long long>(rows) * (slot_hi - slot_lo) * slot_stride;
-  cg::scale_slots_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(src, dst, rows, pitch, slot_stride, slot_lo,
-                                                                          slot_hi, factor);
+  if (slot_stride > 0x7fffffffLL) return fail("slot_stride too large");
+  const long long cols = static_cast<long long>(slot_hi - slot_lo) * slot_stride;
+  const int vec4 = (slot_stride % 4 == 0 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? 1 : 0;
+  const long long work = vec4 ? cols / 4 : cols;
+  long long gx = (work + 255) / 256;
+  const long long want = (static_cast<long long>(d.sm) * 8 + rows - 1) / rows;   // ~8 blocks per SM overall
+  if (gx > want) gx = want;
+  if (gx < 1) gx = 1;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rows < 65535 ? rows : 65535));
+  cg::scale_slots_kernel<<<grid, 256, 0, S(stream)>>>(src, dst, rows, pitch, static_cast<int>(slot_stride), slot_lo,
+                                                      slot_hi, factor, vec4);
   CG_LAUNCH_CHECK();
   return 0;
 }

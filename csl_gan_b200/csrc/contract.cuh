@@ -25,14 +25,14 @@ namespace cg {
 
 constexpr int kBM = 128;          // UMMA M (rows of X per tile)
 constexpr int kBK = 32;           // fp32/tf32 elements per 128-byte swizzle row
-constexpr int kMaxBN = 128;
-constexpr int kStages = 5;
+constexpr int kMaxBN = 256;       // widest MMA N (columns of one accumulator stage)
+constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = 256;    // 2 accumulator stages x 128 fp32 columns
+constexpr int kTmemCols = 512;    // 2 accumulator stages x 256 fp32 columns (all of TMEM; 1 CTA / SM)
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kXTileBytes = kBM * kBK * 4;       // 16 KB
-constexpr int kYTileBytes = kMaxBN * kBK * 4;    // 16 KB (BN <= 128 rows used)
+constexpr int kYTileBytes = kMaxBN * kBK * 4;    // 32 KB (ks stacked tap tiles of BN rows, ks*BN <= 256)
 constexpr int kStageBytes = kXTileBytes + kYTileBytes;
 constexpr int kEpiBufFloats = 32 * 33;           // per epilogue warp transpose buffer
 constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiWarps * kEpiBufFloats * 4 + 256;
@@ -40,6 +40,7 @@ constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kEpiWa
 struct ContractParams {
   int M, n_mtiles;
   int BN, n_rb, KWC;
+  int ks, n_khg, NT;     // taps stacked per item, tap groups, MMA N = ks*BN
   int C, KH, KW;
   int tap_row0[CG_MAX_KH];
   int tap_coloff[CG_MAX_KH];
@@ -65,8 +66,8 @@ __device__ __forceinline__ ItemCoord decode_item(const ContractParams& p, long l
   long long t = item / p.n_mtiles;
   c.rb = static_cast<int>(t % p.n_rb);
   t /= p.n_rb;
-  c.kh = static_cast<int>(t % p.KH);
-  c.g = static_cast<int>(t / p.KH);
+  c.kh = static_cast<int>(t % p.n_khg) * p.ks;      // first tap of the group
+  c.g = static_cast<int>(t / p.n_khg);
   if (p.group_mode == CG_GROUP_SAMPLE) {
     c.base_slot = p.slot_lo + c.g;
     c.n_seg = p.n_seg;
@@ -121,7 +122,7 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t stage_tx = static_cast<uint32_t>(kXTileBytes + p.BN * kBK * 4);
+  const uint32_t sub_bytes = static_cast<uint32_t>(p.BN * kBK * 4);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -131,18 +132,24 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         const int xrow = c.mt * kBM;
-        const int yrow = p.tap_row0[c.kh] + c.rb * p.BN;
+        const int ntap = min(p.ks, p.KH - c.kh);             // taps really present in this group
+        const uint32_t stage_tx = static_cast<uint32_t>(kXTileBytes) + static_cast<uint32_t>(ntap) * sub_bytes;
         for (int s = 0; s < c.n_seg; ++s) {
           const long long slot = c.base_slot + static_cast<long long>(s) * c.seg_stride;
           const long long xcol0 = slot * p.x_slot_stride;
-          const long long ycol0 = slot * p.y_slot_stride + p.tap_coloff[c.kh];
+          const long long ycol0 = slot * p.y_slot_stride;
           for (int kb = 0; kb < p.nkb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* xs = tiles + stage * kStageBytes;
             uint8_t* ys = xs + kXTileBytes;
             mbar_expect_tx(&full_bar[stage], stage_tx);
             tma_load_2d(xs, &tmap_x, &full_bar[stage], static_cast<int32_t>(xcol0 + kb * kBK), xrow);
-            tma_load_2d(ys, &tmap_y, &full_bar[stage], static_cast<int32_t>(ycol0 + kb * kBK), yrow);
+            for (int t = 0; t < ntap; ++t) {
+              // tap kh = a shifted window (column offset) of the plane group starting at tap_row0[kh]
+              tma_load_2d(ys + t * sub_bytes, &tmap_y, &full_bar[stage],
+                          static_cast<int32_t>(ycol0 + p.tap_coloff[c.kh + t] + kb * kBK),
+                          p.tap_row0[c.kh + t] + c.rb * p.BN);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -151,7 +158,7 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kBM, static_cast<uint32_t>(p.BN));
+      const uint32_t idesc = umma_idesc_tf32(kBM, static_cast<uint32_t>(p.NT));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -193,17 +200,20 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kMaxBN);
       const int row = c.mt * kBM + ew * 32 + lane;          // gradient row handled by this thread
-      const int col_base = c.rb * p.BN;                     // column inside the tap group
-      const int ncols = min(p.BN, p.KWC - col_base);        // valid columns of this tile
+      const int col_base = c.rb * p.BN;                     // first column inside each tap group
+      const int ncols = min(p.BN, p.KWC - col_base);        // valid columns of each stacked sub-tile
+      const int ntap = min(p.ks, p.KH - c.kh);
+      const int nt_valid = ntap * p.BN;                     // accumulator columns that hold real taps
 
       if (p.epi == CG_EPI_SUMSQ) {
         float ss = 0.f;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        for (int c0 = 0; c0 < nt_valid; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
+          const int within = c0 % p.BN;                     // BN is a multiple of 16: a chunk never straddles taps
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < ncols) ss = fmaf(v[j], v[j], ss);
+            if (within + j < ncols) ss = fmaf(v[j], v[j], ss);
         }
         tc_fence_before();
         __syncwarp();
@@ -216,23 +226,24 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         // out[m][kh*KWC + col]: transpose 32 rows x 32 cols through smem so each row is one
         // coalesced 128-byte reduction
         const long long ld = static_cast<long long>(p.KH) * p.KWC;
-        float* obase = p.out + static_cast<long long>(c.kh) * p.KWC + col_base;
         const int row0 = c.mt * kBM + ew * 32;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int c0 = 0; c0 < nt_valid; c0 += 32) {
           float v[16];
           tmem_ld16(taddr + c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) tbuf[lane * 33 + j] = v[j];
-          if (c0 + 16 < p.BN) {
+          if (c0 + 16 < nt_valid) {
             tmem_ld16(taddr + c0 + 16, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) tbuf[lane * 33 + 16 + j] = v[j];
           }
           __syncwarp();
-          const int col = c0 + lane;
-          if (col < ncols) {
+          const int cj = c0 + lane;                         // accumulator column of this lane
+          const int sub = cj / p.BN, within = cj - sub * p.BN;
+          if (cj < nt_valid && within < ncols) {
+            float* o = p.out + static_cast<long long>(c.kh + sub) * p.KWC + col_base + within;
             for (int r = 0; r < 32; ++r) {
-              if (row0 + r < p.M) atomicAdd(obase + static_cast<long long>(row0 + r) * ld + col, tbuf[r * 33 + lane]);
+              if (row0 + r < p.M) atomicAdd(o + static_cast<long long>(row0 + r) * ld, tbuf[r * 33 + lane]);
             }
           }
           __syncwarp();
@@ -244,18 +255,19 @@ contract_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         // CG_EPI_STORE: out[g][m][c][kh][kw]
         const int khkw = p.KH * p.KW;
         float* obase = p.out + static_cast<long long>(c.g) * p.out_group_stride +
-                       static_cast<long long>(row) * p.C * khkw + c.kh * p.KW;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                       static_cast<long long>(row) * p.C * khkw;
+        for (int c0 = 0; c0 < nt_valid; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
+          const int sub = c0 / p.BN, within = c0 - sub * p.BN;
           if (row < p.M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int col = col_base + c0 + j;
-              if (c0 + j < ncols) {
+              if (within + j < ncols) {
+                const int col = col_base + within + j;
                 const int kw = col / p.C;
                 const int ch = col - kw * p.C;
-                obase[static_cast<long long>(ch) * khkw + kw] = v[j];
+                obase[static_cast<long long>(ch) * khkw + (c.kh + sub) * p.KW + kw] = v[j];
               }
             }
           }

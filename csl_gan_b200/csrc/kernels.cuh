@@ -143,6 +143,48 @@ __global__ void stage_unfold_kernel(const float* __restrict__ src, const __grid_
   }
 }
 
+// Fast path: one block stages `cpb` input planes of one sample through shared memory (input read
+// once, coalesced) and writes all n_rho*KW kw-planes of those channels (coalesced rows of Hs*Wop).
+// grid (ceil(C/cpb), B), dynamic smem = cpb*H*W floats.
+__global__ void stage_unfold_smem_kernel(const float* __restrict__ src, const __grid_constant__ UnfoldParams p,
+                                         float* __restrict__ dst, int cpb) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y;
+  const int c0 = blockIdx.x * cpb;
+  const int nc = min(cpb, p.C - c0);
+  const int hw = p.H * p.W;
+  const float* base = src + (static_cast<long long>(n) * p.C + c0) * hw;
+  const int tot_in = nc * hw;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (tot_in & 3) == 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    float4* s4 = reinterpret_cast<float4*>(sm);
+    for (int i = threadIdx.x; i < (tot_in >> 2); i += blockDim.x) s4[i] = __ldg(b4 + i);
+  } else {
+    for (int i = threadIdx.x; i < tot_in; i += blockDim.x) sm[i] = base[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int per = p.Hs * p.Wop;
+  const int n_out_rows = p.n_rho * p.KW * nc;
+  const long long col0 = static_cast<long long>(p.slot0 + n) * per;
+  for (int orow = warp; orow < n_out_rows; orow += nwarps) {
+    const int cc = orow % nc;
+    const int t = orow / nc;
+    const int kw = t % p.KW, j = t / p.KW;
+    const float* plane = sm + cc * hw;
+    float* drow = dst + (static_cast<long long>(j * p.KW + kw) * p.C + c0 + cc) * p.dst_pitch + col0;
+    const int hoff = p.sh * p.a_min + p.rho[j];
+    const int woff = kw * p.dw - p.pw;
+    for (int i = lane; i < per; i += 32) {
+      const int hs = i / p.Wop, ow = i - hs * p.Wop;
+      const int h = p.sh * hs + hoff, w = ow * p.sw + woff;
+      float v = 0.f;
+      if (ow < p.Wo && h >= 0 && h < p.H && w >= 0 && w < p.W) v = p.scale * plane[h * p.W + w];
+      drow[i] = round_tf32(v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // row reductions
 // ------------------------------------------------------------------------------------------
@@ -239,19 +281,31 @@ __global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_param
   }
 }
 
-// dst[r][slot*stride + q] = tf32(src * factor[slot]); float4 when everything is 4-aligned
+// dst[r][slot*stride + q] = tf32(src * factor[slot]); grid (col chunks, rows); float4 when 4-aligned
 __global__ void scale_slots_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows,
-                                   long long pitch, long long slot_stride, int slot_lo, int slot_hi,
-                                   const float* __restrict__ factor) {
+                                   long long pitch, int slot_stride, int slot_lo, int slot_hi,
+                                   const float* __restrict__ factor, int vec4) {
   const long long cols = static_cast<long long>(slot_hi - slot_lo) * slot_stride;
   const long long col0 = static_cast<long long>(slot_lo) * slot_stride;
-  const long long total = static_cast<long long>(rows) * cols;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / cols, cidx = i - r * cols;
-    const int slot = slot_lo + static_cast<int>(cidx / slot_stride);
-    const long long off = r * pitch + col0 + cidx;
-    dst[off] = round_tf32(src[off] * factor[slot]);
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float* s = src + static_cast<long long>(r) * pitch + col0;
+    float* d = dst + static_cast<long long>(r) * pitch + col0;
+    if (vec4) {
+      const long long n4 = cols >> 2;
+      for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+           i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float f = __ldg(factor + slot_lo + static_cast<int>((i << 2) / slot_stride));
+        float4 v = __ldg(reinterpret_cast<const float4*>(s) + i);
+        v.x = round_tf32(v.x * f); v.y = round_tf32(v.y * f); v.z = round_tf32(v.z * f); v.w = round_tf32(v.w * f);
+        reinterpret_cast<float4*>(d)[i] = v;
+      }
+    } else {
+      for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < cols;
+           i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float f = __ldg(factor + slot_lo + static_cast<int>(i / slot_stride));
+        d[i] = round_tf32(s[i] * f);
+      }
+    }
   }
 }
 

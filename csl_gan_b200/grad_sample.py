@@ -216,9 +216,13 @@ class LayerPlan:
         """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots."""
         st = L.stream_ptr(out_w.device)
         d = self._desc(self.Xc)
+        # mirror of the tile choice in cg_contract (csrc/abi.cu)
         kwc = self.KW * self.Cn
-        bn = min(128, _round_up(kwc, 16))
-        n_tiles = ((self.M + 127) // 128) * self.KH * ((kwc + bn - 1) // bn)
+        parts = (kwc + 255) // 256
+        bn = _round_up((kwc + parts - 1) // parts, 16)
+        n_rb = (kwc + bn - 1) // bn
+        ks = max(1, min(self.KH, 256 // bn)) if n_rb == 1 else 1
+        n_tiles = ((self.M + 127) // 128) * ((self.KH + ks - 1) // ks) * n_rb
         if self.kind == "linear":
             # contraction index = slot; units of 32 slots
             u_lo, u_hi = slot_lo // KBLK, (slot_hi + KBLK - 1) // KBLK

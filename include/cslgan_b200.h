@@ -129,7 +129,7 @@ typedef struct cg_contract_desc {
   int epi;
   float* out;
   long long out_group_stride;  /* CG_EPI_STORE: floats between groups                      */
-  int block_n;                 /* 0 = choose automatically; else multiple of 16, <= 128    */
+  int block_n;                 /* 0 = choose automatically; else multiple of 16, <= 256    */
   int max_ctas;                /* 0 = one CTA per SM                                       */
 } cg_contract_desc;
 
