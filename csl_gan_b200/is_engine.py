@@ -116,13 +116,8 @@ class ISPrivacyEngine:
             world = dist.get_world_size(self.process_group)
             # the sensitivity is that of the GLOBAL mean gradient: every rank needs the global g before
             # ||g|| is differentiated (two exchange steps)
-            flat = torch.cat([gi.detach().reshape(-1) for gi in g])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)
-            flat /= world
-            g_glob, off = [], 0
-            for gi in g:
-                g_glob.append(flat[off:off + gi.numel()].view_as(gi))
-                off += gi.numel()
+            from .dist import allreduce_flat
+            g_glob = [t / world for t in allreduce_flat([gi.detach() for gi in g], group=self.process_group)]
         else:
             g_glob = [gi.detach() for gi in g]
         for p, gi in zip(params, g_glob):
@@ -144,9 +139,8 @@ class ISPrivacyEngine:
             constant, d||g_global||/dx_i = <v, d g_local / dx_i> / world."""
             if world == 1:
                 return row_l2_norm(local.reshape(1, -1)).sum()
-            n = row_l2_norm(glob.reshape(1, -1)).sum()
-            v = torch.where(n > 0, glob.reshape(-1) / n, torch.zeros_like(glob.reshape(-1)))
-            return (local.reshape(-1) * v).sum() / world
+            from .dist import global_norm_proxy
+            return global_norm_proxy(local.reshape(-1), glob.reshape(-1), world)
 
         if self.per_param:
             rows, maxes = [], []

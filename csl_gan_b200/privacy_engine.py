@@ -629,15 +629,11 @@ class PrivacyEngine:
         the global one; noise is then drawn identically on every rank from the shared Philox
         (seed, offset), so all replicas apply the same update."""
         import torch.distributed as dist
-        pg = self.process_group
-        flat = torch.cat([p.summed_grad.reshape(-1) for p in self._params])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg)
-        off = 0
-        for p in self._params:
-            n = p.numel()
-            p.summed_grad = flat[off:off + n].view_as(p)
-            off += n
-        return bs * dist.get_world_size(pg)
+        from .dist import allreduce_flat
+        red = allreduce_flat([p.summed_grad for p in self._params], group=self.process_group)
+        for p, r in zip(self._params, red):
+            p.summed_grad = r
+        return bs * dist.get_world_size(self.process_group)
 
     def zero_grad(self):
         """Patched optimizer.zero_grad (reference train.py:245): also drops captured state."""

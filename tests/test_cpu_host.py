@@ -1,0 +1,160 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, host-only entry
+points work without a GPU, the product path fails loudly without CUDA, accountant / options / Philox
+restatement behave, and the lazy grad_sample protocol objects have the right shapes."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import csl_gan_b200 as cg
+from csl_gan_b200 import _lib as L
+from csl_gan_b200 import accountant, options
+from oracle import philox as PH
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from csl_gan_b200 import build
+    build.build()                      # nvcc cross-compiles without a GPU
+    return L.load()
+
+
+def test_library_exports_every_symbol_declared_in_the_header(lib):
+    hdr = open(os.path.join(ROOT, "include", "cslgan_b200.h")).read()
+    declared = set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/cslgan_b200.h but not exported"
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    assert lib.cg_version() >= 100
+
+
+def test_plan_unfold_host_logic(lib):
+    # 5x5 stride 2 pad 2 on 64x64 (every conv of the reference critics): two row residues, taps at -1..1
+    g, p = L.plan_unfold(3, 64, 64, 5, 5, 2, 2, 2, 2, 1, 1, 32, 32)
+    assert (p.n_rho, p.Hs, p.Wop, p.rows, p.slot_stride, p.a_min) == (2, 34, 32, 30, 34 * 32, -1)
+    assert list(p.tap_row0)[:5] == [0, 15, 0, 15, 0]
+    assert list(p.tap_coloff)[:5] == [0, 0, 32, 32, 64]
+    # 14x14 output: window rows padded to 16 so every TMA box starts 16-byte aligned
+    g, p = L.plan_unfold(1, 28, 28, 5, 5, 2, 2, 2, 2, 1, 1, 14, 14)
+    assert p.Wop == 16 and p.slot_stride == 16 * 16 and list(p.tap_coloff)[:5] == [0, 0, 16, 16, 32]
+    # stride 1: a single residue, one plane row per kw
+    g, p = L.plan_unfold(8, 10, 10, 3, 3, 1, 1, 1, 1, 1, 1, 10, 10)
+    assert p.n_rho == 1 and p.rows == 3 * 8 and p.Hs == 12 and list(p.tap_coloff)[:3] == [0, 12, 24]
+    # brute-force: every (kh, oh) maps to the input row the convolution reads
+    for (H, k, s, pad, d) in [(64, 5, 2, 2, 1), (13, 3, 2, 0, 2), (10, 4, 3, 1, 1), (9, 3, 1, 1, 1)]:
+        Ho = (H + 2 * pad - d * (k - 1) - 1) // s + 1
+        g, p = L.plan_unfold(2, H, H, k, k, s, s, pad, pad, d, d, Ho, Ho)
+        for kh in range(k):
+            j = p.tap_row0[kh] // (k * 2)
+            for oh in range(Ho):
+                hs = p.tap_coloff[kh] // p.Wop + oh
+                assert s * (hs + p.a_min) + p.rho[j] == oh * s - pad + kh * d
+    with pytest.raises(L.CslGanCudaError):
+        L.plan_unfold(1, 8, 8, 99, 3, 1, 1, 0, 0, 1, 1, 1, 6)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    D = cg.discriminators.MNISTVanillaD(n_classes=0)
+    with pytest.raises(cg.CslGanCudaError):
+        cg.PrivacyEngine(D, batch_size=4, sample_size=100, noise_multiplier=1.0, max_grad_norm=1.0)
+    with pytest.raises(cg.CslGanCudaError):
+        cg.ISPrivacyEngine(D, batch_size=4, sample_size=100, noise_multiplier=1.0)
+    with pytest.raises(cg.CslGanCudaError):
+        cg.row_l2_norm(torch.zeros(3, 4))
+    with pytest.raises(cg.CslGanCudaError):
+        cg.l2_clip(torch.zeros(3, 4), 1.0)
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "csl_gan_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f"{fn} references the oracle"
+
+
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors for philox4x32-10."""
+    def run(c, k):
+        return [int(x) for x in PH.philox4x32_10(np.array(c, dtype=np.uint32), np.array(k, dtype=np.uint32))]
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_stream_layout_and_moments():
+    n = 200_000
+    z = PH.torch_cuda_standard_normal(n, seed=1234, offset=0)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    # offset bookkeeping: grid = min(148*8, ceil(n/256)); increment = ((n-1)/(256*grid*4)+1)*4
+    assert PH.torch_cuda_offset_increment(1) == 4
+    assert PH.torch_cuda_offset_increment(256 * 1184 * 4) == 4
+    assert PH.torch_cuda_offset_increment(256 * 1184 * 4 + 1) == 8
+    # a later offset continues a thread's own stream: element i at offset 4 equals what the same
+    # thread would draw on its second loop trip at offset 0
+    a = PH.torch_cuda_standard_normal(256 * 1184 * 4 + 8, 7, 0)
+    b = PH.torch_cuda_standard_normal(8, 7, 4, sm_count=148)
+    # thread idx t, second trip -> linear index 256*1184*4 + t (component 0)
+    np.testing.assert_array_equal(a[256 * 1184 * 4: 256 * 1184 * 4 + 8], b[:8])
+
+
+def test_accountant_matches_closed_forms_and_is_monotone():
+    # q = 1: RDP of the plain Gaussian mechanism is alpha / (2 sigma^2)
+    assert accountant.compute_rdp(1.0, 2.0, 1, 8.0) == pytest.approx(8.0 / (2 * 4.0))
+    orders = [1 + x / 10.0 for x in range(1, 100)] + list(range(12, 64))
+    r1 = accountant.compute_rdp(0.01, 1.1, 100, orders)
+    r2 = accountant.compute_rdp(0.01, 1.1, 200, orders)
+    np.testing.assert_allclose(r2, 2 * r1)
+    e1, a1 = accountant.get_privacy_spent(orders, r1, 1e-5)
+    e2, _ = accountant.get_privacy_spent(orders, r2, 1e-5)
+    assert 0 < e1 < e2 and a1 in orders
+    e_hi, _ = accountant.get_privacy_spent(orders, accountant.compute_rdp(0.01, 0.6, 100, orders), 1e-5)
+    assert e_hi > e1                       # less noise -> more privacy loss
+    ec, _ = accountant.get_privacy_spent(orders, r1, 1e-5, conversion="classic")
+    assert ec >= e1                        # the improved conversion is never looser
+    # integer and fractional orders agree at the boundary
+    lo = accountant.compute_rdp(0.02, 1.3, 1, 5.0)
+    hi = accountant.compute_rdp(0.02, 1.3, 1, 5.0 + 1e-9)
+    assert hi == pytest.approx(lo, rel=1e-5)
+    # the well-known DP-SGD reference point (q=256/60000, sigma=1.1, 60 epochs, delta=1e-5) is eps ~ 3.0 (classic ~3.5)
+    steps = int(60 * 60000 / 256)
+    big = list(orders) + list(range(64, 256))
+    eps, _ = accountant.get_privacy_spent(big, accountant.compute_rdp(256 / 60000, 1.1, steps, big), 1e-5)
+    assert 2.5 < eps < 3.6
+
+
+def test_options_defaults_and_derived_flags():
+    o = options.parse(["MNIST", "-dpm", "gc", "--conditional", "--sigma", "10"])
+    assert (o.batch_size, o.clipping_param, o.sigma, o.grad_clip_mode, o.grad_clip_split) == (600, 4.0, 10.0, "standard", True)
+    assert o.use_dp and o.per_sample_grad and o.is_acgan and o.use_aux_loss and not o.use_grad_clip_per_layer
+    o = options.parse(["CelebA", "-dpm", "gc", "-gcm", "adaptive-pl", "-nms", "32"])
+    assert o.use_grad_clip_per_layer and o.clipping_param_per_layer == [1000, 200, 1000, 100, 1000, 100, 1000, 5, 2500]
+    assert o.penalty == ["WGAN-GP"] and o.adaptive_scalar == 1.5 and o.batch_size == 128
+    o = options.parse(["CelebA", "-dpm", "is", "-ispp", "False", "-nms", "32"])
+    assert o.imm_sens_per_param is True        # reference quirk: False counts as unset (options.py:95)
+    assert not o.per_sample_grad
+    with pytest.raises(Exception):
+        options.parse(["CelebA", "-dpm", "gc"])                    # penalty on public data needs -nms / -pss
+    with pytest.raises(NotImplementedError):
+        options.parse(["MNIST", "-dpm", "tm"])
+    with pytest.raises(Exception):
+        options.parse(["MNIST", "-dpm", "is", "-ispp", "True", "-issm", "constant-pl"])
+
+
+def test_rel_lazy_grad_sample_shapes_do_not_need_a_gpu():
+    class FakeEngine:
+        _cur_B = 7
+        _params = [torch.zeros(3, 4)]
+        def _n_passes_view(self):
+            return 2
+    v = cg.GradSampleView(FakeEngine(), 0)
+    assert v.size(1) == 7 and tuple(v.shape) == (2, 7, 3, 4) and len(v) == 2 and v.dim() == 4
