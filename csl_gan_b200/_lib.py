@@ -34,6 +34,19 @@ class UnfoldPlan(C.Structure):
                 ("rho", C.c_int * CG_MAX_KH), ("a_min", C.c_int)]
 
 
+class GhostPlan(C.Structure):
+    _fields_ = [("n_rh", C.c_int), ("n_rw", C.c_int), ("Hs", C.c_int), ("Ws", C.c_int), ("ah_min", C.c_int),
+                ("aw_min", C.c_int), ("Cp", C.c_int), ("rho_h", C.c_int * CG_MAX_KH), ("rho_w", C.c_int * CG_MAX_KH),
+                ("tap_plane", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("tap_hoff", C.c_int * (CG_MAX_KH * CG_MAX_KH)),
+                ("tap_woff", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("slot_stride", C.c_longlong)]
+
+
+class GhostDesc(C.Structure):
+    _fields_ = [("Xt", C.c_void_p), ("xt_pitch", C.c_longlong), ("xt_rows", C.c_longlong),
+                ("Yt", C.c_void_p), ("n_slots_total", C.c_int), ("O", C.c_int),
+                ("slot0", C.c_int), ("n_slots", C.c_int), ("norm2", C.c_void_p), ("max_ctas", C.c_int)]
+
+
 class ContractDesc(C.Structure):
     _fields_ = [
         ("X", C.c_void_p), ("x_pitch", C.c_longlong), ("x_rows", C.c_int), ("x_cols", C.c_longlong),
@@ -61,6 +74,12 @@ _PROTOS = {
     "cg_stage_unfold": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(UnfoldGeom), C.POINTER(UnfoldPlan), C.c_float,
                                   C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cg_contract": (C.c_int, [C.POINTER(ContractDesc), C.c_void_p]),
+    "cg_plan_ghost": (C.c_int, [C.POINTER(UnfoldGeom), C.POINTER(GhostPlan)]),
+    "cg_stage_nhwc_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong,
+                                     C.c_int, C.c_void_p]),
+    "cg_stage_nhwc_s2d": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cg_ghost_norm": (C.c_int, [C.POINTER(GhostDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
     "cg_outer_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     "cg_row_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
@@ -86,7 +105,7 @@ EXPORTED_SYMBOLS = tuple(_PROTOS)
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
-_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold"}
+_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost"}
 
 
 def load() -> C.CDLL:
@@ -168,6 +187,15 @@ def plan_unfold(C_, H, W, KH, KW, sh, sw, ph, pw, dh, dw, Ho, Wo):
     p = UnfoldPlan()
     call("cg_plan_unfold", C.byref(g), C.byref(p))
     return g, p
+
+
+def plan_ghost(geom: UnfoldGeom):
+    """GhostPlan for the geometry, or None when it is outside the ghost-norm envelope."""
+    lib = load()
+    p = GhostPlan()
+    if lib.cg_plan_ghost(C.byref(geom), C.byref(p)) != 0:
+        return None
+    return p
 
 
 def device_info():

@@ -9,6 +9,7 @@
 
 #include "../../include/cslgan_b200.h"
 #include "contract.cuh"
+#include "ghost.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -109,6 +110,36 @@ int make_tmap(CUtensorMap* tm, const float* base, long long rows, long long cols
 float recip(double div) { return div > 0.0 ? 1.0f / static_cast<float>(div) : 0.0f; }
 
 int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// generic tiled tensor map (fp32, SWIZZLE_128B); dims/strides innermost first, strides in bytes for dims 1..rank-1
+int make_tmap_nd(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                 const cuuint32_t* box) {
+  EncodeTiledFn enc;
+  if (get_encode(&enc)) return 1;
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor base pointer must be 16-byte aligned");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, static_cast<int>(r));
+  return 0;
+}
+
+// residues / shifts of one spatial axis: index = s*(pos + a) + rho  for tap k  (k*d - pad = s*a + rho)
+void axis_plan(int K, int s, int d, int pad, int* a, int* j_of, int* rho, int* n_rho, int* a_min, int* a_max) {
+  *n_rho = 0; *a_min = 1 << 30; *a_max = -(1 << 30);
+  for (int k = 0; k < K; ++k) {
+    const int r = k * d - pad;
+    a[k] = floor_div(r, s);
+    const int rr = r - a[k] * s;
+    if (a[k] < *a_min) *a_min = a[k];
+    if (a[k] > *a_max) *a_max = a[k];
+    int j = -1;
+    for (int t = 0; t < *n_rho; ++t) if (rho[t] == rr) j = t;
+    if (j < 0) { j = *n_rho; rho[(*n_rho)++] = rr; }
+    j_of[k] = j;
+  }
+}
 
 }  // namespace
 
@@ -279,6 +310,121 @@ int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
   long long grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
   if (grid > p.n_items) grid = p.n_items;
   cg::contract_kernel<<<static_cast<int>(grid), cg::kThreads, cg::kSmemBytes, S(stream)>>>(tx, ty, p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan) {
+  if (!g || !plan) return fail("null argument");
+  if (g->KH < 1 || g->KH > CG_MAX_KH || g->KW < 1 || g->KW > CG_MAX_KH) return fail("unsupported filter size");
+  const int Q = g->Ho * g->Wo;
+  if (Q < 1 || Q > 128 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128 (got %d)", Q);
+  if (g->Wo > 256 || g->Ho > 256) return fail("window extent too large for a TMA box");
+  if (static_cast<long long>(g->H) * g->W > 768) return fail("input plane too large for the s2d staging kernel");
+  memset(plan, 0, sizeof(*plan));
+  int ah[CG_MAX_KH], aw[CG_MAX_KH], jh[CG_MAX_KH], jw[CG_MAX_KH];
+  int ah_min, ah_max, aw_min, aw_max;
+  axis_plan(g->KH, g->sh, g->dh, g->ph, ah, jh, plan->rho_h, &plan->n_rh, &ah_min, &ah_max);
+  axis_plan(g->KW, g->sw, g->dw, g->pw, aw, jw, plan->rho_w, &plan->n_rw, &aw_min, &aw_max);
+  plan->ah_min = ah_min; plan->aw_min = aw_min;
+  plan->Hs = g->Ho + ah_max - ah_min;
+  plan->Ws = g->Wo + aw_max - aw_min;
+  plan->Cp = (g->C + 3) / 4 * 4;
+  plan->slot_stride = static_cast<long long>(plan->Hs) * plan->Ws * plan->Cp;
+  for (int kh = 0; kh < g->KH; ++kh)
+    for (int kw = 0; kw < g->KW; ++kw) {
+      const int t = kh * g->KW + kw;
+      plan->tap_plane[t] = jh[kh] * plan->n_rw + jw[kw];
+      plan->tap_hoff[t] = ah[kh] - ah_min;
+      plan->tap_woff[t] = aw[kw] - aw_min;
+    }
+  return 0;
+}
+
+int cg_stage_nhwc_rows(const float* src, int B, int R, int Q, float scale, float* dst, long long dst_pitch, int slot0,
+                       cg_stream_t stream) {
+  if (B <= 0 || R <= 0 || Q <= 0) return 0;
+  if (B > 65535) return fail("batch too large for the staging grid");
+  dim3 grid((Q + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  cg::stage_nhwc_rows_kernel<<<grid, block, 0, S(stream)>>>(src, R, Q, scale, dst, dst_pitch, slot0);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_stage_nhwc_s2d(const float* src, int B, const cg_unfold_geom* g, const cg_ghost_plan* plan, float scale,
+                      float* dst, int n_slots_total, int slot0, cg_stream_t stream) {
+  if (!g || !plan) return fail("null argument");
+  if (B <= 0) return 0;
+  if (B > 65535) return fail("batch too large for the staging grid");
+  cg::S2dParams p;
+  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W; p.Cp = plan->Cp;
+  p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sh = g->sh; p.sw = g->sw;
+  p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
+  for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
+  p.scale = scale; p.slot0 = slot0;
+  p.slot_stride = plan->slot_stride;
+  p.plane_stride = plan->slot_stride * n_slots_total;
+  const size_t smem = 32 * (static_cast<size_t>(g->H) * g->W + 1) * sizeof(float);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::stage_nhwc_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[dev] = true;
+  }
+  dim3 grid((plan->Cp + 31) / 32, B);
+  cg::stage_nhwc_s2d_kernel<<<grid, 256, smem, S(stream)>>>(src, p, dst);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream) {
+  if (!d || !g || !plan) return fail("null argument");
+  DevInfo dv;
+  if (dev_info(&dv)) return 1;
+  if (dv.major != 10) return fail("cg_ghost_norm needs an sm_100-class device (found sm_%d%d)", dv.major, dv.minor);
+  if (d->n_slots <= 0) return 0;
+  const int Q = g->Ho * g->Wo;
+  if (Q < 1 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128");
+  cg::GhostParams p;
+  memset(&p, 0, sizeof(p));
+  p.Q = Q; p.ns = 128 / Q; p.O = d->O; p.C = g->C; p.KH = g->KH; p.KW = g->KW;
+  for (int t = 0; t < g->KH * g->KW; ++t) {
+    p.tap_plane[t] = plan->tap_plane[t]; p.tap_hoff[t] = plan->tap_hoff[t]; p.tap_woff[t] = plan->tap_woff[t];
+  }
+  p.slot0 = d->slot0; p.n_slots = d->n_slots;
+  p.n_items = (d->n_slots + p.ns - 1) / p.ns;
+  p.norm2 = d->norm2;
+
+  CUtensorMap tx, ty;
+  {
+    if ((d->xt_pitch * 4) % 16) return fail("Xt pitch must be a multiple of 4 floats");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->O), static_cast<cuuint64_t>(d->xt_rows)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(d->xt_pitch) * 4};
+    cuuint32_t box[2] = {32, 128};
+    if (make_tmap_nd(&tx, d->Xt, 2, dims, str, box)) return 1;
+  }
+  {
+    const cuuint64_t Cp = plan->Cp;
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(g->C), static_cast<cuuint64_t>(plan->Ws),
+                          static_cast<cuuint64_t>(plan->Hs), static_cast<cuuint64_t>(d->n_slots_total),
+                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw)};
+    cuuint64_t str[4] = {Cp * 4, Cp * 4 * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
+                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
+    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(g->Wo), static_cast<cuuint32_t>(g->Ho),
+                         static_cast<cuuint32_t>(p.ns), 1};
+    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box)) return 1;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::ghost_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kGSmemBytes));
+    attr_set[dev] = true;
+  }
+  int grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
+  if (grid > p.n_items) grid = p.n_items;
+  cg::ghost_norm_kernel<<<grid, cg::kGThreads, cg::kGSmemBytes, S(stream)>>>(tx, ty, p);
   CG_LAUNCH_CHECK();
   return 0;
 }

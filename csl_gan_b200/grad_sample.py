@@ -53,6 +53,8 @@ class LayerPlan:
         self.sig = None
         self.Bpad = 0
         self.max_passes = 0
+        self.use_ghost = True
+        self.gplan = None
 
     # ------------------------------------------------------------------ geometry / buffers
     def _setup(self, act: torch.Tensor, Bpad: int, max_passes: int):
@@ -117,6 +119,12 @@ class LayerPlan:
             self.bias_rows = torch.zeros((S, self.bias_len), device=dev) if self.b_idx is not None else None
             if self.kind == "convT" and self.b_idx is not None:
                 self._bias_scratch = torch.empty((self.bias_len, _round_up(Bpad * H * W, 4)), device=dev)
+            # ghost norms (Gram matrices from channels-last staging) when Q = Ho*Wo divides 128
+            self.gplan = L.plan_ghost(self.geom) if self.use_ghost else None
+            if self.gplan is not None:
+                self.Xt = torch.zeros((S * self.Q, _round_up(self.M, 4)), device=dev)
+                n_planes = self.gplan.n_rh * self.gplan.n_rw
+                self.Yt = torch.zeros(n_planes * S * self.gplan.slot_stride, device=dev)
         self.nkb = self.Qpad // KBLK if self.kind != "linear" else 1
         # gradient-natural accumulation buffer T[m][kh][kw*C + c] (Linear: == parameter layout)
         self.T = torch.zeros((self.M, self.KH * self.KW * self.Cn), device=dev)
@@ -141,9 +149,15 @@ class LayerPlan:
         elif self.kind == "conv":
             L.call("cg_stage_unfold", L.ptr(act), B, C.byref(self.geom), C.byref(self.plan), 1.0,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
+            if self.gplan is not None:
+                L.call("cg_stage_nhwc_s2d", L.ptr(act), B, C.byref(self.geom), C.byref(self.gplan), 1.0,
+                       L.ptr(self.Yt), self.S, slot0, st)
         else:  # convT: the activation is the plain operand
             L.call("cg_stage_rows", L.ptr(act), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, 1.0,
                    L.ptr(self.X), self.X.stride(0), slot0, None, st)
+            if self.gplan is not None:
+                L.call("cg_stage_nhwc_rows", L.ptr(act), B, self.M, self.Q, 1.0, L.ptr(self.Xt),
+                       self.Xt.stride(0), slot0, st)
 
     def capture_backprop(self, grad_out: torch.Tensor, pass_idx: int, scale: float):
         g = L.require_cuda_f32(grad_out.detach(), f"{self.name}: backprop")
@@ -157,9 +171,15 @@ class LayerPlan:
             # rowsum is indexed by absolute slot inside the kernel -> pass the buffer base
             L.call("cg_stage_rows", L.ptr(g), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, scale,
                    L.ptr(self.X), self.X.stride(0), slot0, L.ptr(self.bias_rows), st)
+            if self.gplan is not None:
+                L.call("cg_stage_nhwc_rows", L.ptr(g), B, self.M, self.Q, scale, L.ptr(self.Xt),
+                       self.Xt.stride(0), slot0, st)
         else:
             L.call("cg_stage_unfold", L.ptr(g), B, C.byref(self.geom), C.byref(self.plan), scale,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
+            if self.gplan is not None:
+                L.call("cg_stage_nhwc_s2d", L.ptr(g), B, C.byref(self.geom), C.byref(self.gplan), scale,
+                       L.ptr(self.Yt), self.S, slot0, st)
             if self.bias_rows is not None:
                 hw = g.shape[2] * g.shape[3]
                 L.call("cg_stage_rows", L.ptr(g), B, self.bias_len, hw, hw, hw, hw, scale,
@@ -188,6 +208,14 @@ class LayerPlan:
             if n_joint != 1:
                 raise NotImplementedError("joint (accum_passes=True) norms for Linear layers")
             L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
+            return
+        if self.gplan is not None and n_joint == 1:
+            gd = L.GhostDesc()
+            gd.Xt, gd.xt_pitch, gd.xt_rows = L.ptr(self.Xt), self.Xt.stride(0), self.Xt.shape[0]
+            gd.Yt, gd.n_slots_total, gd.O = L.ptr(self.Yt), self.S, self.M
+            gd.slot0, gd.n_slots = slot0, B
+            gd.norm2, gd.max_ctas = L.ptr(norm2_row[slot0:]), 0
+            L.call("cg_ghost_norm", C.byref(gd), C.byref(self.geom), C.byref(self.gplan), st)
             return
         d = self._desc(self.X)
         d.group_mode, d.n_groups = L.GROUP_SAMPLE, B

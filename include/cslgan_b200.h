@@ -141,6 +141,45 @@ int cg_outer_rows(const float* X, long long x_pitch, const float* Y, long long y
                   int slot0, int B, float* out, cg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Ghost norms for layers with few window positions (Q = Ho*Wo divides 128):
+ *   ||G_n||^2 = sum_{q,q'} (Xn^T Xn)[q,q'] (Un^T Un)[q,q']
+ * Both Gram matrices run on tcgen05 for 128/Q samples per tile from channels-last staging:
+ *   Xt[(slot*Q + q)][o]                         (cg_stage_nhwc_rows)
+ *   Yt[plane(jh,jw)][slot][hs][ws][c]           (cg_stage_nhwc_s2d; space-to-depth so every filter
+ *                                                tap is a unit-stride window = one 5-D TMA box)
+ * Same result as cg_contract(CG_EPI_SUMSQ) (replaces calc_sample_norms, reference train.py:311-314),
+ * without the O x P-element epilogue per sample.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cg_ghost_plan {
+  int n_rh, n_rw;            /* distinct row / column residues                               */
+  int Hs, Ws;                /* staged plane extent                                          */
+  int ah_min, aw_min;
+  int Cp;                    /* channels rounded up to 4 (16-byte pitch)                     */
+  int rho_h[CG_MAX_KH], rho_w[CG_MAX_KH];
+  int tap_plane[CG_MAX_KH * CG_MAX_KH], tap_hoff[CG_MAX_KH * CG_MAX_KH], tap_woff[CG_MAX_KH * CG_MAX_KH];
+  long long slot_stride;     /* floats per slot inside a plane = Hs*Ws*Cp                    */
+} cg_ghost_plan;
+
+/* returns non-zero (with a message) when the geometry is outside the ghost path's envelope */
+int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan);
+
+int cg_stage_nhwc_rows(const float* src, int B, int R, int Q, float scale, float* dst, long long dst_pitch,
+                       int slot0, cg_stream_t stream);
+int cg_stage_nhwc_s2d(const float* src, int B, const cg_unfold_geom* g, const cg_ghost_plan* plan, float scale,
+                      float* dst, int n_slots_total, int slot0, cg_stream_t stream);
+
+typedef struct cg_ghost_desc {
+  const float* Xt; long long xt_pitch; long long xt_rows;   /* [n_slots_total*Q][O]        */
+  const float* Yt; int n_slots_total;                       /* plane-major staged tensor   */
+  int O;
+  int slot0, n_slots;                                       /* slots to process            */
+  float* norm2;                                             /* norm2[slot - slot0] +=      */
+  int max_ctas;
+} cg_ghost_desc;
+
+int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Small reductions around the contraction
  * ------------------------------------------------------------------------------------------- */
 

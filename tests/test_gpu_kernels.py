@@ -136,6 +136,35 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d)
     assert ((out.cpu() - ref).norm() / ref.norm()).item() < 1e-3
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p", [
+    (5, 256, 512, 8, 8, 5, 2, 2),        # D64 blocks.3: Q = 16, 8 samples per tile, ragged last group
+    (3, 128, 256, 16, 16, 5, 2, 2),      # D64 blocks.2: Q = 64, 2 samples per tile
+    (9, 6, 10, 8, 8, 3, 2, 1),           # Q = 16, C not a multiple of 4 or 32, O not a multiple of 32
+    (4, 8, 8, 4, 4, 3, 1, 1),            # stride 1, Q = 16
+    (2, 16, 24, 16, 32, 3, 2, 1),        # Q = 128, one sample per tile, non-square
+])
+def test_ghost_norms_match_direct_and_oracle(B, Cin, Cout, H, W, k, s, p):
+    from csl_gan_b200.grad_sample import LayerPlan
+    conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p)
+    gw_ref, _ = O.conv2d_grad_sample(conv, A, Bp)
+    ref_n2 = gw_ref.reshape(B, -1).double().pow(2).sum(1).numpy()
+    conv = conv.to(DEV)
+    out = {}
+    for ghost in (True, False):
+        plan = LayerPlan("conv", conv, 0, 1)
+        plan.use_ghost = ghost
+        plan.capture_activation(A.to(DEV), 1, 32, 2)          # second pass: exercises slot offsets
+        plan.capture_backprop(Bp.to(DEV), 1, 1.0)
+        assert (plan.gplan is not None) == ghost
+        norm2 = torch.zeros(64, device=DEV)
+        plan.weight_norm2(norm2, 1, B)
+        torch.cuda.synchronize()
+        assert float(norm2[:32].abs().sum()) == 0.0 and float(norm2[32 + B:].abs().sum()) == 0.0
+        out[ghost] = norm2[32:32 + B].cpu().double().numpy()
+    np.testing.assert_allclose(out[True], ref_n2, rtol=2e-3)
+    np.testing.assert_allclose(out[True], out[False], rtol=2e-3)
+
+
 def test_conv_transpose_per_sample_grads():
     from csl_gan_b200.grad_sample import LayerPlan
     g = torch.Generator().manual_seed(3)
