@@ -269,7 +269,10 @@ def main():
 
     wl = args.workload
     B = args.batch or (512 if wl == "celeba_d64_gc" else 600)
+    torch.backends.cudnn.benchmark = True                     # reference train.py:28
     D, real_h, fake_h, y_h, cfg = make_workload(wl, B, dev, seed=rank)
+    if wl == "celeba_d64_gc":
+        D = D.to(memory_format=torch.channels_last)          # cuDNN's native tensor-core layout for the critic itself
     real_pin, fake_pin = real_h.pin_memory(), fake_h.pin_memory()
     y_dev = None if y_h is None else y_h.to(dev)
     opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9) if wl == "celeba_d64_gc" else (0.9, 0.999))

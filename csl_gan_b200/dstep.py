@@ -80,10 +80,11 @@ class DStepResult:
 class DiscriminatorStep:
     def __init__(self, opt, D: nn.Module, d_optimizer, privacy_engine=None,
                  public_batch: Optional[Callable[[int, Optional[torch.Tensor]], Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None,
-                 collect_stats: bool = False):
+                 collect_stats: bool = False, skip_weight_grads: bool = True):
         self.opt, self.D, self.opt_d, self.engine = opt, D, d_optimizer, privacy_engine
         self.public_batch = public_batch
         self.collect_stats = collect_stats
+        self.skip_weight_grads = skip_weight_grads
 
     # ------------------------------------------------------------------ losses (train.py:342-358)
     def _fake_loss(self, fake_img, y):
@@ -165,7 +166,8 @@ class DiscriminatorStep:
             res.d_real_aux_loss, res.d_real_aux = d_real_aux_loss.detach(), d_real_aux.detach()
 
         if opt.per_sample_grad and use_dp:
-            d_loss.backward()
+            # grad_outputs of every captured layer, without the (unused) batch-summed weight gradients
+            eng.backward(d_loss) if self.skip_weight_grads else d_loss.backward()
             eng.disable_hooks()
         if use_gc:
             if self.collect_stats:

@@ -271,12 +271,25 @@ class LayerPlan:
         d.slot_lo, d.slot_hi, d.spg = u_lo, u_hi, spg
         d.n_seg, d.seg_stride = 1, 1
         conv_like = self.kind != "linear"
-        target = self.T if conv_like else out_w
-        if conv_like or not accumulate:
+        # the GEMM accumulates in the gradient-natural layout [m][kh][kw][c]; that IS the memory order
+        # of a channels_last weight, so such parameters need no permute at all
+        natural = None
+        if conv_like and out_w.dim() == 4 and not out_w.is_contiguous() \
+                and out_w.is_contiguous(memory_format=torch.channels_last):
+            natural = out_w.permute(0, 2, 3, 1)
+        if not conv_like:
+            target = out_w
+        elif natural is not None:
+            target = natural
+        else:
+            target = self.T
+        if target is self.T or not accumulate:
             target.zero_()
         d.epi, d.out, d.out_group_stride = L.EPI_ACCUM, L.ptr(target), 0
         L.call("cg_contract", C.byref(d), st)
-        if conv_like:
+        if target is self.T:
+            if not out_w.is_contiguous():
+                raise L.CslGanCudaError(f"{self.name}: unsupported weight memory layout {out_w.stride()}")
             L.call("cg_permute_accum", L.ptr(self.T), L.ptr(out_w), self.M, self.Cn, self.KH, self.KW,
                    1 if accumulate else 0, st)
 

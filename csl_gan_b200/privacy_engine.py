@@ -317,6 +317,7 @@ class PrivacyEngine:
             self._factors_valid = False
             if output.requires_grad:
                 scale = float(B) if self.loss_reduction == "mean" else 1.0
+                self._outputs.append(output)
 
                 def grad_hook(g, plan=plan, pass_idx=pass_idx, scale=scale):
                     if self.hooks_enabled:
@@ -347,7 +348,21 @@ class PrivacyEngine:
                     plan.capture_backprop(gout, ps, float(B) if self.loss_reduction == "mean" else 1.0)
                     self._bp_seen.add((plan, ps))
 
+    def backward(self, loss: torch.Tensor):
+        """Backward pass that stops at the captured layer outputs: the per-sample machinery needs every
+        layer's grad_output but never the batch-summed weight gradients autograd would also compute
+        (the reference's d_loss.backward(), train.py:387, computes them and then overwrites p.grad in
+        step()).  Skipping them removes the cuDNN wgrad kernels from the D step."""
+        outs = self._outputs
+        if not outs:
+            raise RuntimeError("backward(loss) needs a forward pass with hooks enabled")
+        torch.autograd.backward(loss, inputs=outs)
+        for o in outs:
+            o.grad = None
+        self._outputs = []
+
     def _reset_capture(self):
+        self._outputs: List[torch.Tensor] = []
         self._pass_count: Dict[LayerPlan, int] = {}
         self._pass_B: Dict[int, int] = {}
         self._bp_seen = set()

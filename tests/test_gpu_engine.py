@@ -358,6 +358,30 @@ def test_gradient_penalty_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(got, g["wgan_gp_grad_norms"], rtol=5e-3, atol=1e-6)
 
 
+def test_engine_backward_skips_weight_grads_and_handles_channels_last():
+    """engine.backward(loss) delivers the same per-sample machinery inputs as loss.backward() without
+    autograd's own weight gradients; a channels_last critic gives the same result."""
+    D, shape, ncls, lo = make("mnist_dcrn")
+    B = 6
+    real, fake, y = batch(shape, ncls, lo, B, seed=21)
+    ref = run_oracle(copy.deepcopy(D), real, fake, y, B, 0.3)
+    for cl in (False, True):
+        Dg = copy.deepcopy(D).to(DEV)
+        if cl:
+            Dg = Dg.to(memory_format=torch.channels_last)
+        opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+        eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=1000, noise_multiplier=0.0, max_grad_norm=0.3,
+                               num_private_passes=1, auto_clip_and_accum_on_step=False)
+        eng.attach(opt)
+        eng.backward(d_loss(Dg, real.to(DEV), fake.to(DEV), None))
+        assert all(p.grad is None for p in Dg.parameters())          # autograd never touched the weights
+        eng.disable_hooks()
+        eng.clip(); eng.accum_grads_across_passes(); eng.accumulate_batch()
+        opt.step()
+        for p, g in zip(Dg.parameters(), ref["grads"]):
+            assert rel(p.grad, g) < REL_TOL
+
+
 def test_engine_rejects_cpu_module_and_batchnorm():
     D, *_ = make("mnist_uncond")
     with pytest.raises(cg.CslGanCudaError):
