@@ -38,7 +38,18 @@ class GhostPlan(C.Structure):
     _fields_ = [("n_rh", C.c_int), ("n_rw", C.c_int), ("Hs", C.c_int), ("Ws", C.c_int), ("ah_min", C.c_int),
                 ("aw_min", C.c_int), ("Cp", C.c_int), ("rho_h", C.c_int * CG_MAX_KH), ("rho_w", C.c_int * CG_MAX_KH),
                 ("tap_plane", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("tap_hoff", C.c_int * (CG_MAX_KH * CG_MAX_KH)),
-                ("tap_woff", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("slot_stride", C.c_longlong)]
+                ("tap_woff", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("slot_stride", C.c_longlong),
+                ("merged", C.c_int), ("Cs", C.c_int), ("n_taps", C.c_int)]
+
+
+ClPlan = GhostPlan
+
+
+class ClDesc(C.Structure):
+    _fields_ = [("Xt", C.c_void_p), ("xt_pitch", C.c_longlong), ("xt_rows", C.c_longlong), ("M", C.c_int),
+                ("Yt", C.c_void_p), ("n_slots_total", C.c_int),
+                ("group_mode", C.c_int), ("n_groups", C.c_int), ("slot_lo", C.c_int), ("slot_hi", C.c_int),
+                ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong), ("max_ctas", C.c_int)]
 
 
 class GhostDesc(C.Structure):
@@ -75,11 +86,17 @@ _PROTOS = {
                                   C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cg_contract": (C.c_int, [C.POINTER(ContractDesc), C.c_void_p]),
     "cg_plan_ghost": (C.c_int, [C.POINTER(UnfoldGeom), C.POINTER(GhostPlan)]),
-    "cg_stage_nhwc_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong,
-                                     C.c_int, C.c_void_p]),
-    "cg_stage_nhwc_s2d": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float,
-                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cg_ghost_norm": (C.c_int, [C.POINTER(GhostDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
+    "cg_plan_cl": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int, C.POINTER(GhostPlan)]),
+    "cg_stage_xt": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                              C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p]),
+    "cg_stage_yt": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                              C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p]),
+    "cg_cl_contract": (C.c_int, [C.POINTER(ClDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
+    "cg_outer_rows_cl": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_void_p]),
     "cg_outer_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     "cg_row_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
@@ -105,7 +122,7 @@ EXPORTED_SYMBOLS = tuple(_PROTOS)
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
-_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost"}
+_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost", "cg_plan_cl"}
 
 
 def load() -> C.CDLL:
@@ -196,6 +213,23 @@ def plan_ghost(geom: UnfoldGeom):
     if lib.cg_plan_ghost(C.byref(geom), C.byref(p)) != 0:
         return None
     return p
+
+
+def plan_cl(geom: UnfoldGeom, merged: bool) -> GhostPlan:
+    p = GhostPlan()
+    call("cg_plan_cl", C.byref(geom), 1 if merged else 0, C.byref(p))
+    return p
+
+
+def cl_supported(Ho: int, Wo: int) -> bool:
+    """Mirror of cl_kblock() in csrc/abi.cu: can the window grid be tiled into 32-position k-blocks?"""
+    Q = Ho * Wo
+    if Q >= 32:
+        if Q % 32:
+            return False
+        w = min(Wo, 32)
+        return Wo % w == 0 and 32 % w == 0 and Ho % (32 // w) == 0
+    return 32 % Q == 0
 
 
 def device_info():

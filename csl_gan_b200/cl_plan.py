@@ -1,0 +1,261 @@
+"""Channels-last capture / contraction plan of one layer (the main path; `grad_sample.LayerPlan`
+dispatches here whenever the layer's window grid can be tiled into 32-position k-blocks).
+
+Capture is one element-wise pass per tensor when the critic runs in `torch.channels_last` (the layout
+cuDNN prefers on Blackwell): backprops -> Xt[(slot, q)][m], activations -> space-to-depth
+Yt[plane][slot][hs][ws][c].  Other layouts are read through their strides (slower, still correct).
+Replaces the same fork operations as the legacy plan (upstream opacus `_capture_activations`,
+`_compute_*_grad_sample`; reference train.py:382-387, 399).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+MERGE_BELOW = 16       # inputs with fewer channels fold the filter columns into the channel axis
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _strides4(t: torch.Tensor):
+    """(sn, sc, sh, sw) of a [B, C, H, W] or [B, C] tensor, in elements."""
+    if t.dim() == 2:
+        return t.stride(0), t.stride(1), 0, 0
+    return t.stride(0), t.stride(1), t.stride(2), t.stride(3)
+
+
+def _channels_fastest(t: torch.Tensor) -> torch.Tensor:
+    """The staging kernels coalesce when the channel stride is 1; convert anything else once."""
+    if t.dim() == 4 and t.stride(1) != 1 and t.shape[1] > 1:
+        return t.contiguous(memory_format=torch.channels_last)
+    if t.dim() == 2 and t.stride(1) != 1:
+        return t.contiguous()
+    return t
+
+
+class ClLayerPlan:
+    def __init__(self, name: str, layer: nn.Module, kind: str, w_idx: int, b_idx: Optional[int], use_ghost: bool = True):
+        self.name, self.layer, self.kind, self.w_idx, self.b_idx = name, layer, kind, w_idx, b_idx
+        self.use_ghost = use_ghost
+
+    # ------------------------------------------------------------------ geometry / buffers
+    @staticmethod
+    def geometry(layer: nn.Module, kind: str, act_shape):
+        """(Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M) of the layer's unfolded operand."""
+        if kind == "linear":
+            return (layer.in_features, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 1, layer.out_features)
+        kh, kw = layer.kernel_size
+        sh, sw = layer.stride
+        ph, pw = layer.padding
+        dh, dw = layer.dilation
+        if kind == "conv":
+            Cn, H, W = act_shape[1], act_shape[2], act_shape[3]
+            Ho = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+            Wo = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+            M = layer.out_channels
+        else:
+            Hin, Win = act_shape[2], act_shape[3]
+            oph, opw = layer.output_padding
+            H = (Hin - 1) * sh - 2 * ph + dh * (kh - 1) + oph + 1
+            W = (Win - 1) * sw - 2 * pw + dw * (kw - 1) + opw + 1
+            Cn, Ho, Wo, M = layer.out_channels, Hin, Win, layer.in_channels
+        return (Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M)
+
+    def setup(self, act: torch.Tensor, Bpad: int, max_passes: int):
+        dev = act.device
+        self.Bpad, self.max_passes = Bpad, max_passes
+        S = self.S = Bpad * max_passes
+        (Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M) = self.geometry(self.layer, self.kind, act.shape)
+        self.Cn, self.KH, self.KW, self.Ho, self.Wo, self.M = Cn, kh, kw, Ho, Wo, M
+        self.Q = Ho * Wo
+        self.geom = L.UnfoldGeom(Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo)
+        ghost_ok = (self.use_ghost and self.kind != "linear" and self.Q <= 128 and 128 % self.Q == 0
+                    and Wo <= 256 and Ho <= 256)
+        # thin inputs (the 3-channel image) fold the filter columns into the channel axis so a 32-wide
+        # channel chunk is not 90% padding; small-Q layers keep the plain layout the ghost norms need
+        merged = self.kind != "linear" and Cn < MERGE_BELOW and kw > 1 and not ghost_ok
+        self.plan = L.plan_cl(self.geom, merged)
+        self.n_planes = self.plan.n_rh * self.plan.n_rw
+        # chunk-major staging: Xt[m/32][slot*Q + q][32], Yt[plane*n_cb + c/32][slot][hs][ws][32]
+        self.x_chunks = _round_up(M, 32) // 32
+        self.x_rows = S * self.Q
+        self.Xt = torch.zeros((self.x_chunks, self.x_rows, 32), device=dev)
+        self.Xc = torch.zeros((self.x_chunks, self.x_rows, 32), device=dev)
+        self.n_cb = self.plan.Cp // 32
+        self.Yt = torch.zeros(self.n_planes * self.n_cb * S * self.plan.slot_stride, device=dev)
+        self.bias_len = layer_bias_len(self.layer, self.kind)
+        self.bias_rows = torch.zeros((S, self.bias_len), device=dev) if self.b_idx is not None else None
+        if self.kind == "linear":
+            self.asq = torch.zeros(S, device=dev)
+            self.bsq = torch.zeros(S, device=dev)
+        # gradient-natural accumulation buffer T[m][tap][c'] (== parameter layout for Linear and for
+        # channels_last conv weights when kw is not merged)
+        self.ldT = self.plan.n_taps * self.plan.Cs
+        self.T = torch.zeros((M, self.ldT), device=dev)
+        # ghost norms when Q | 128 (needs the un-merged plan, which is what small-Q layers have)
+        self.ghost = ghost_ok
+        if self.kind == "convT" and self.b_idx is not None:
+            self._bias_scratch = torch.empty((_round_up(self.bias_len, 32) // 32, Bpad * H * W, 32), device=dev)
+            self._HW = (H, W)
+
+    # ------------------------------------------------------------------ capture
+    def _stage_x(self, t: torch.Tensor, slot0: int, scale: float, bias_rows, sumsq):
+        t = _channels_fastest(t)
+        sn, sm, sh, sw = _strides4(t)
+        L.call("cg_stage_xt", L.ptr(t), sn, sm, sh, sw, t.shape[0], self.M, self.Ho, self.Wo, scale,
+               L.ptr(self.Xt), self.x_rows, slot0, L.ptr(bias_rows), L.ptr(sumsq), L.stream_ptr(t.device))
+
+    def _stage_y(self, t: torch.Tensor, slot0: int, scale: float):
+        t = _channels_fastest(t)
+        st = L.stream_ptr(t.device)
+        if self.kind == "linear":
+            # Q = 1: Yt is [p/32][slot][p%32], the same chunked row layout as Xt; the row kernel also
+            # yields ||a||^2 for the closed-form norms
+            L.call("cg_stage_xt", L.ptr(t), t.stride(0), t.stride(1), 0, 0, t.shape[0], self.Cn, 1, 1, scale,
+                   L.ptr(self.Yt), self.S, slot0, None, L.ptr(self.asq), st)
+            return
+        sn, sc, sh, sw = _strides4(t)
+        L.call("cg_stage_yt", L.ptr(t), sn, sc, sh, sw, t.shape[0], C.byref(self.geom), C.byref(self.plan), scale,
+               L.ptr(self.Yt), self.S, slot0, st)
+
+    def capture_activation(self, act: torch.Tensor, pass_idx: int):
+        slot0 = pass_idx * self.Bpad
+        if self.kind == "convT":
+            self._stage_x(act, slot0, 1.0, None, None)
+        else:
+            self._stage_y(act, slot0, 1.0)
+
+    def capture_backprop(self, g: torch.Tensor, pass_idx: int, scale: float):
+        slot0 = pass_idx * self.Bpad
+        if self.kind == "convT":
+            self._stage_y(g, slot0, scale)
+            if self.bias_rows is not None:
+                gg = _channels_fastest(g)
+                sn, sm, sh, sw = _strides4(gg)
+                H, W = self._HW
+                L.call("cg_stage_xt", L.ptr(gg), sn, sm, sh, sw, gg.shape[0], self.bias_len, H, W, scale,
+                       L.ptr(self._bias_scratch), self._bias_scratch.shape[1], 0,
+                       L.ptr(self.bias_rows[slot0:]), None, L.stream_ptr(g.device))
+        else:
+            self._stage_x(g, slot0, scale, self.bias_rows, self.bsq if self.kind == "linear" else None)
+
+    # ------------------------------------------------------------------ launches
+    def _desc(self, X: torch.Tensor) -> L.ClDesc:
+        d = L.ClDesc()
+        d.Xt, d.xt_pitch, d.xt_rows, d.M = L.ptr(X), 32, self.x_rows, self.M
+        d.Yt, d.n_slots_total = L.ptr(self.Yt), self.S
+        d.max_ctas = 0
+        return d
+
+    def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
+        slot0 = pass_idx * self.Bpad
+        st = L.stream_ptr(norm2_row.device)
+        if n_joint != 1:
+            raise NotImplementedError("joint (accum_passes=True) norms")
+        if self.kind == "linear":
+            L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
+            return
+        if self.ghost:
+            gd = L.GhostDesc()
+            gd.Xt, gd.xt_pitch, gd.xt_rows = L.ptr(self.Xt), 32, self.x_rows
+            gd.Yt, gd.n_slots_total, gd.O = L.ptr(self.Yt), self.S, self.M
+            gd.slot0, gd.n_slots = slot0, B
+            gd.norm2, gd.max_ctas = L.ptr(norm2_row[slot0:]), 0
+            L.call("cg_ghost_norm", C.byref(gd), C.byref(self.geom), C.byref(self.plan), st)
+            return
+        d = self._desc(self.Xt)
+        d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
+        d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
+        L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
+
+    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int):
+        slot0 = pass_idx * self.Bpad
+        st = L.stream_ptr(norm2_row.device)
+        if self.kind == "linear":
+            norm2_row[slot0:slot0 + B].copy_(self.bsq[slot0:slot0 + B])
+            return
+        R = self.bias_rows.shape[1]
+        L.call("cg_row_sumsq", L.ptr(self.bias_rows[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
+
+    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
+        """Xc = tf32(Xt * factor[slot]): every chunk of Xt is a row of slot-sized (Q*32) segments."""
+        L.call("cg_scale_slots", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * 32, self.Q * 32,
+               slot_lo, slot_hi, L.ptr(factor_row), L.stream_ptr(factor_row.device))
+
+    def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
+        st = L.stream_ptr(out_w.device)
+        d = self._desc(self.Xc)
+        # tiles per K range (mirror of cg_cl_contract) -> split K so the grid covers the machine ~2x
+        n_cb, n_taps = self.n_cb, self.plan.n_taps
+        if n_cb >= 8:
+            parts = (n_cb + 7) // 8
+            cpt = (n_cb + parts - 1) // parts
+            n_nt = n_taps * ((n_cb + cpt - 1) // cpt)
+        else:
+            tpt = min(8 // n_cb, n_taps)
+            parts = (n_taps + tpt - 1) // tpt
+            tpt = (n_taps + parts - 1) // parts
+            n_nt = (n_taps + tpt - 1) // tpt
+        n_tiles = ((self.M + 127) // 128) * n_nt
+        units = (slot_hi - slot_lo) * max(1, self.Q // 32) if self.Q >= 32 else (slot_hi - slot_lo + 32 // self.Q - 1) // (32 // self.Q)
+        want = max(1, (2 * sm_count) // max(1, n_tiles))
+        n_groups = max(1, min(want, units // 4 if units >= 4 else 1))
+        d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SPLITK, n_groups, slot_lo, slot_hi
+        # where does the gradient-natural layout T[m][tap][c'] already equal the parameter's memory?
+        natural = None
+        if self.kind == "linear":
+            natural = out_w
+        elif (out_w.dim() == 4 and not out_w.is_contiguous()
+              and out_w.is_contiguous(memory_format=torch.channels_last)):
+            # channels_last weight memory is [m][kh][kw][c] = T[m][tap][c'] (merged: c' = kw*C + c)
+            natural = out_w.permute(0, 2, 3, 1)
+        target = natural if natural is not None else self.T
+        if target is self.T or not accumulate:
+            target.zero_()
+        d.epi, d.out, d.out_group_stride = L.EPI_ACCUM, L.ptr(target), 0
+        L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
+        if target is self.T:
+            dst = out_w
+            if not out_w.is_contiguous():
+                if not (out_w.dim() == 4 and out_w.is_contiguous(memory_format=torch.channels_last)):
+                    raise L.CslGanCudaError(f"{self.name}: unsupported weight memory layout {out_w.stride()}")
+                dst = torch.empty(out_w.shape, device=out_w.device)      # contiguous scratch, copied below
+            # T[m][kh][kw*C + c] (merged or not: the column index is (kh, kw, c) either way)
+            L.call("cg_permute_accum", L.ptr(self.T), L.ptr(dst), self.M, self.Cn, self.KH, self.KW,
+                   1 if (accumulate and dst is out_w) else 0, st)
+            if dst is not out_w:
+                out_w.add_(dst) if accumulate else out_w.copy_(dst)
+
+    def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
+                          accumulate: bool):
+        R = self.bias_rows.shape[1]
+        L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row), slot_lo, slot_hi, R,
+               L.ptr(out_b), 1 if accumulate else 0, L.stream_ptr(out_b.device))
+
+    def materialize(self, pass_idx: int, B: int) -> torch.Tensor:
+        slot0 = pass_idx * self.Bpad
+        w = self.layer.weight
+        out = torch.zeros((B,) + tuple(w.shape), device=w.device)
+        st = L.stream_ptr(w.device)
+        if self.kind == "linear":
+            L.call("cg_outer_rows_cl", L.ptr(self.Xt), self.x_rows, L.ptr(self.Yt), self.S,
+                   self.M, self.Cn, slot0, B, L.ptr(out), st)
+            return out
+        d = self._desc(self.Xt)
+        d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
+        d.epi, d.out, d.out_group_stride = L.EPI_STORE, L.ptr(out), w.numel()
+        L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
+        return out
+
+
+def layer_bias_len(layer: nn.Module, kind: str) -> int:
+    if kind == "linear":
+        return layer.out_features
+    return layer.out_channels

@@ -10,6 +10,7 @@
 #include "../../include/cslgan_b200.h"
 #include "contract.cuh"
 #include "ghost.cuh"
+#include "cl.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -113,13 +114,13 @@ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // generic tiled tensor map (fp32, SWIZZLE_128B); dims/strides innermost first, strides in bytes for dims 1..rank-1
 int make_tmap_nd(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                 const cuuint32_t* box) {
+                 const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc;
   if (get_encode(&enc)) return 1;
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor base pointer must be 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, static_cast<int>(r));
   return 0;
@@ -314,68 +315,53 @@ int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
   return 0;
 }
 
-int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan) {
+int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan) {
   if (!g || !plan) return fail("null argument");
   if (g->KH < 1 || g->KH > CG_MAX_KH || g->KW < 1 || g->KW > CG_MAX_KH) return fail("unsupported filter size");
-  const int Q = g->Ho * g->Wo;
-  if (Q < 1 || Q > 128 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128 (got %d)", Q);
-  if (g->Wo > 256 || g->Ho > 256) return fail("window extent too large for a TMA box");
-  if (static_cast<long long>(g->H) * g->W > 768) return fail("input plane too large for the s2d staging kernel");
+  if (g->sh < 1 || g->sw < 1 || g->dh < 1 || g->dw < 1) return fail("stride/dilation must be >= 1");
   memset(plan, 0, sizeof(*plan));
   int ah[CG_MAX_KH], aw[CG_MAX_KH], jh[CG_MAX_KH], jw[CG_MAX_KH];
   int ah_min, ah_max, aw_min, aw_max;
   axis_plan(g->KH, g->sh, g->dh, g->ph, ah, jh, plan->rho_h, &plan->n_rh, &ah_min, &ah_max);
-  axis_plan(g->KW, g->sw, g->dw, g->pw, aw, jw, plan->rho_w, &plan->n_rw, &aw_min, &aw_max);
-  plan->ah_min = ah_min; plan->aw_min = aw_min;
+  plan->ah_min = ah_min;
   plan->Hs = g->Ho + ah_max - ah_min;
-  plan->Ws = g->Wo + aw_max - aw_min;
-  plan->Cp = (g->C + 3) / 4 * 4;
-  plan->slot_stride = static_cast<long long>(plan->Hs) * plan->Ws * plan->Cp;
-  for (int kh = 0; kh < g->KH; ++kh)
-    for (int kw = 0; kw < g->KW; ++kw) {
-      const int t = kh * g->KW + kw;
-      plan->tap_plane[t] = jh[kh] * plan->n_rw + jw[kw];
-      plan->tap_hoff[t] = ah[kh] - ah_min;
-      plan->tap_woff[t] = aw[kw] - aw_min;
+  plan->merged = merged ? 1 : 0;
+  if (merged) {
+    // filter columns live in the channel axis: one plane per row residue, window rows of exactly Wo
+    plan->n_rw = 1; plan->rho_w[0] = 0; plan->aw_min = 0;
+    plan->Ws = g->Wo;
+    plan->Cs = g->KW * g->C;
+    plan->n_taps = g->KH;
+    for (int kh = 0; kh < g->KH; ++kh) {
+      plan->tap_plane[kh] = jh[kh];
+      plan->tap_hoff[kh] = ah[kh] - ah_min;
+      plan->tap_woff[kh] = 0;
     }
-  return 0;
-}
-
-int cg_stage_nhwc_rows(const float* src, int B, int R, int Q, float scale, float* dst, long long dst_pitch, int slot0,
-                       cg_stream_t stream) {
-  if (B <= 0 || R <= 0 || Q <= 0) return 0;
-  if (B > 65535) return fail("batch too large for the staging grid");
-  dim3 grid((Q + 31) / 32, (R + 31) / 32, B), block(32, 8);
-  cg::stage_nhwc_rows_kernel<<<grid, block, 0, S(stream)>>>(src, R, Q, scale, dst, dst_pitch, slot0);
-  CG_LAUNCH_CHECK();
-  return 0;
-}
-
-int cg_stage_nhwc_s2d(const float* src, int B, const cg_unfold_geom* g, const cg_ghost_plan* plan, float scale,
-                      float* dst, int n_slots_total, int slot0, cg_stream_t stream) {
-  if (!g || !plan) return fail("null argument");
-  if (B <= 0) return 0;
-  if (B > 65535) return fail("batch too large for the staging grid");
-  cg::S2dParams p;
-  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W; p.Cp = plan->Cp;
-  p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sh = g->sh; p.sw = g->sw;
-  p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
-  for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
-  p.scale = scale; p.slot0 = slot0;
-  p.slot_stride = plan->slot_stride;
-  p.plane_stride = plan->slot_stride * n_slots_total;
-  const size_t smem = 32 * (static_cast<size_t>(g->H) * g->W + 1) * sizeof(float);
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CG_CHECK(cudaGetDevice(&dev));
-  if (!attr_set[dev]) {
-    CG_CHECK(cudaFuncSetAttribute(cg::stage_nhwc_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set[dev] = true;
+  } else {
+    axis_plan(g->KW, g->sw, g->dw, g->pw, aw, jw, plan->rho_w, &plan->n_rw, &aw_min, &aw_max);
+    plan->aw_min = aw_min;
+    plan->Ws = g->Wo + aw_max - aw_min;
+    plan->Cs = g->C;
+    plan->n_taps = g->KH * g->KW;
+    for (int kh = 0; kh < g->KH; ++kh)
+      for (int kw = 0; kw < g->KW; ++kw) {
+        const int t = kh * g->KW + kw;
+        plan->tap_plane[t] = jh[kh] * plan->n_rw + jw[kw];
+        plan->tap_hoff[t] = ah[kh] - ah_min;
+        plan->tap_woff[t] = aw[kw] - aw_min;
+      }
   }
-  dim3 grid((plan->Cp + 31) / 32, B);
-  cg::stage_nhwc_s2d_kernel<<<grid, 256, smem, S(stream)>>>(src, p, dst);
-  CG_LAUNCH_CHECK();
+  plan->Cp = (plan->Cs + 31) / 32 * 32;
+  plan->slot_stride = static_cast<long long>(plan->Hs) * plan->Ws * 32;   // per 32-channel chunk
   return 0;
+}
+
+int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan) {
+  if (!g || !plan) return fail("null argument");
+  const int Q = g->Ho * g->Wo;
+  if (Q < 1 || Q > 128 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128 (got %d)", Q);
+  if (g->Wo > 256 || g->Ho > 256) return fail("window extent too large for a TMA box");
+  return cg_plan_cl(g, 0, plan);
 }
 
 int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream) {
@@ -398,18 +384,18 @@ int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghos
 
   CUtensorMap tx, ty;
   {
-    if ((d->xt_pitch * 4) % 16) return fail("Xt pitch must be a multiple of 4 floats");
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->O), static_cast<cuuint64_t>(d->xt_rows)};
-    cuuint64_t str[1] = {static_cast<cuuint64_t>(d->xt_pitch) * 4};
-    cuuint32_t box[2] = {32, 128};
-    if (make_tmap_nd(&tx, d->Xt, 2, dims, str, box)) return 1;
+    // Xt[o/32][row][o%32]: a K-major tile = 128 rows of one 32-channel chunk
+    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->O + 31) / 32)};
+    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
+    cuuint32_t box[3] = {32, 128, 1};
+    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box)) return 1;
   }
   {
-    const cuuint64_t Cp = plan->Cp;
-    cuuint64_t dims[5] = {static_cast<cuuint64_t>(g->C), static_cast<cuuint64_t>(plan->Ws),
-                          static_cast<cuuint64_t>(plan->Hs), static_cast<cuuint64_t>(d->n_slots_total),
-                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw)};
-    cuuint64_t str[4] = {Cp * 4, Cp * 4 * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
+    const cuuint64_t n_cb = (g->C + 31) / 32;
+    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                          static_cast<cuuint64_t>(d->n_slots_total),
+                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * n_cb};
+    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
                          static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
     cuuint32_t box[5] = {32, static_cast<cuuint32_t>(g->Wo), static_cast<cuuint32_t>(g->Ho),
                          static_cast<cuuint32_t>(p.ns), 1};
@@ -425,6 +411,200 @@ int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghos
   int grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
   if (grid > p.n_items) grid = p.n_items;
   cg::ghost_norm_kernel<<<grid, cg::kGThreads, cg::kGSmemBytes, S(stream)>>>(tx, ty, p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+// k-block geometry of the channels-last path; returns non-zero when the window grid cannot be tiled
+static int cl_kblock(const cg_unfold_geom* g, int per_sample, int* kb_rows, int* kb_w, int* kb_h, int* kb_s) {
+  const int Q = g->Ho * g->Wo;
+  if (Q >= 32) {
+    if (Q % 32) return fail("channels-last path needs Ho*Wo to be a multiple of 32 or a divisor of 32 (got %d)", Q);
+    int w = g->Wo < 32 ? g->Wo : 32;
+    if (g->Wo % w || 32 % w) return fail("window row length %d cannot be tiled into 32-position k-blocks", g->Wo);
+    *kb_w = w; *kb_h = 32 / w; *kb_s = 1; *kb_rows = 32;
+    if (g->Ho % *kb_h) return fail("window grid %dx%d cannot be tiled into 32-position k-blocks", g->Ho, g->Wo);
+    return 0;
+  }
+  if (32 % Q) return fail("channels-last path needs Ho*Wo to be a multiple of 32 or a divisor of 32 (got %d)", Q);
+  *kb_w = g->Wo; *kb_h = g->Ho;
+  if (per_sample) {
+    if (Q % 8) return fail("per-sample groups need Ho*Wo to be a multiple of 8 (got %d)", Q);
+    *kb_s = 1; *kb_rows = Q;
+  } else {
+    *kb_s = 32 / Q; *kb_rows = 32;
+  }
+  return 0;
+}
+
+int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M, int Ho,
+                int Wo, float scale, float* dst, long long rows_total, int slot0, float* bias_rows, float* sumsq,
+                cg_stream_t stream) {
+  if (B <= 0 || M <= 0) return 0;
+  if (B > 65535) return fail("batch too large for the staging grid");
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const int Q = Ho * Wo;
+  if (bias_rows) CG_CHECK(cudaMemsetAsync(bias_rows + static_cast<long long>(slot0) * M, 0, sizeof(float) * B * M, S(stream)));
+  if (sumsq) CG_CHECK(cudaMemsetAsync(sumsq + slot0, 0, sizeof(float) * B, S(stream)));
+  if (static_cast<long long>(slot0 + B) * Q > rows_total) return fail("Xt too small for slots [%d, %d)", slot0, slot0 + B);
+  int block = ((M < 256 ? M : 256) + 31) / 32 * 32;
+  // positions per block: keep ~8 blocks per SM in flight without shredding the bias sums into atomics
+  int qchunks = static_cast<int>((8LL * d.sm + B - 1) / B);
+  if (qchunks < 1) qchunks = 1;
+  if (qchunks > Q) qchunks = Q;
+  int qpb = (Q + qchunks - 1) / qchunks;
+  dim3 grid((Q + qpb - 1) / qpb, B);
+  const bool vec4 = sm == 1 && (M % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 15) == 0 && M / 4 <= 256;
+  if (vec4) {
+    const int mv = M / 4;
+    int vblock = mv >= 128 ? ((mv + 31) / 32 * 32) : 128;     // at least 128 threads: several positions in parallel
+    if (vblock % mv) vblock = (vblock / mv + 1) * mv;         // whole groups of channel vectors
+    if (vblock > 1024) vblock = mv;
+    cg::stage_xt_vec4_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
+                                                             bias_rows, sumsq, qpb);
+  } else {
+    cg::stage_xt_kernel<<<grid, block, 0, S(stream)>>>(src, sn, sm, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
+                                                       bias_rows, sumsq, qpb);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
+                const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, float* dst, int n_slots_total,
+                int slot0, cg_stream_t stream) {
+  if (!g || !plan) return fail("null argument");
+  if (B <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const int n_planes = plan->n_rh * plan->n_rw;
+  const int n_cb = plan->Cp / 32;
+  if (B > 65535 || n_planes * n_cb > 65535) return fail("problem too large for the staging grid");
+  cg::YtParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;
+  p.sn = sn; p.sc = sc; p.sh_ = sh; p.sw_ = sw;
+  p.Cs = plan->Cs; p.n_cb = n_cb; p.merged = plan->merged; p.KW = g->KW; p.dw = g->dw; p.pw = g->pw;
+  p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sth = g->sh; p.stw = g->sw;
+  p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
+  for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
+  p.scale = scale; p.slot0 = slot0;
+  p.slot_stride = plan->slot_stride;
+  p.chunk_stride = plan->slot_stride * n_slots_total;
+  const int n_pos = plan->Hs * plan->Ws;
+  const bool vec4 = !plan->merged && sc == 1 && (g->C % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec4) {
+    // 256 threads = 32 positions per step; 128 positions per block (4 steps, unrolled -> 4 loads in flight)
+    const int ppb = 128;
+    dim3 grid((n_pos + ppb - 1) / ppb, B, n_planes * n_cb);
+    cg::stage_yt_vec4_kernel<<<grid, 256, 0, S(stream)>>>(src, p, dst, ppb);
+  } else {
+    int gx = (n_pos + 63) / 64;                    // 8 warps per block, 8 positions per warp
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, B, n_planes * n_cb);
+    cg::stage_yt_kernel<<<grid, 256, 0, S(stream)>>>(src, p, dst);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream) {
+  if (!d || !g || !plan) return fail("null argument");
+  DevInfo dv;
+  if (dev_info(&dv)) return 1;
+  if (dv.major != 10) return fail("cg_cl_contract needs an sm_100-class device (found sm_%d%d)", dv.major, dv.minor);
+  if (d->n_groups <= 0) return 0;
+  const int Q = g->Ho * g->Wo;
+  int kb_rows, kb_w, kb_h, kb_s;
+  if (cl_kblock(g, d->group_mode == CG_GROUP_SAMPLE, &kb_rows, &kb_w, &kb_h, &kb_s)) return 1;
+  cg::ClParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.n_mtiles = (d->M + 127) / 128;
+  p.C = plan->Cs; p.n_cb = plan->Cp / 32;
+  p.n_taps = plan->n_taps;
+  if (p.n_cb >= 8) {
+    // wide layers: a tile is up to 8 chunks of ONE tap (one TMA box)
+    const int parts = (p.n_cb + 7) / 8;
+    p.tpt = 1; p.cpt = (p.n_cb + parts - 1) / parts;
+    p.tiles_per_tap = (p.n_cb + p.cpt - 1) / p.cpt;
+    p.n_nt = p.n_taps * p.tiles_per_tap;
+  } else {
+    // narrow layers: a tile stacks whole taps (one TMA box each) up to 8 chunks
+    int tpt = 8 / p.n_cb;
+    if (tpt > p.n_taps) tpt = p.n_taps;
+    const int parts = (p.n_taps + tpt - 1) / tpt;
+    p.tpt = (p.n_taps + parts - 1) / parts; p.cpt = p.n_cb;
+    p.tiles_per_tap = 0;
+    p.n_nt = (p.n_taps + p.tpt - 1) / p.tpt;
+  }
+  for (int t = 0; t < p.n_taps; ++t) {
+    p.tap_plane[t] = plan->tap_plane[t]; p.tap_hoff[t] = plan->tap_hoff[t]; p.tap_woff[t] = plan->tap_woff[t];
+  }
+  p.Q = Q; p.Wo = g->Wo; p.kb_rows = kb_rows; p.kb_s = kb_s;
+  p.nkb_slot = (Q >= 32) ? Q / 32 : 1;
+  p.group_mode = d->group_mode; p.n_groups = d->n_groups; p.slot_lo = d->slot_lo;
+  if (d->group_mode == CG_GROUP_SPLITK) {
+    if (d->slot_hi <= d->slot_lo) return 0;
+    if (kb_s > 1) {
+      if (d->slot_lo % kb_s) return fail("slot_lo must be a multiple of %d for this layer", kb_s);
+      p.u_lo = d->slot_lo / kb_s;
+      p.u_hi = (d->slot_hi + kb_s - 1) / kb_s;
+    } else {
+      p.u_lo = static_cast<long long>(d->slot_lo) * p.nkb_slot;
+      p.u_hi = static_cast<long long>(d->slot_hi) * p.nkb_slot;
+    }
+    const long long units = p.u_hi - p.u_lo;
+    p.upg = (units + d->n_groups - 1) / d->n_groups;
+    p.n_groups = static_cast<int>((units + p.upg - 1) / p.upg);
+  }
+  p.epi = d->epi; p.out = d->out; p.out_group_stride = d->out_group_stride;
+  p.ldT = static_cast<long long>(p.n_taps) * p.C;
+  p.KH = g->KH; p.KW = g->KW; p.Corig = g->C; p.merged = plan->merged;
+  p.n_items = static_cast<long long>(p.n_groups) * p.n_nt * p.n_mtiles;
+
+  CUtensorMap tx, ty;
+  {
+    // Xt[m/32][row][m%32]: one box = kb_rows rows of four consecutive chunks -> smem [chunk][row][32]
+    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->M + 31) / 32)};
+    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
+    cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kb_rows), 4};
+    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  }
+  {
+    // Yt[plane*n_cb + c/32][slot][hs][ws][c%32]: one box = a tap window of `cpt` consecutive chunks
+    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                          static_cast<cuuint64_t>(d->n_slots_total),
+                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * p.n_cb};
+    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
+                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
+    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(kb_w), static_cast<cuuint32_t>(kb_h),
+                         static_cast<cuuint32_t>(kb_s), static_cast<cuuint32_t>(p.cpt)};
+    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::cl_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kClSmemBytes));
+    attr_set[dev] = true;
+  }
+  long long grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
+  if (grid > p.n_items) grid = p.n_items;
+  cg::cl_contract_kernel<<<static_cast<int>(grid), cg::kClThreads, cg::kClSmemBytes, S(stream)>>>(tx, ty, p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_outer_rows_cl(const float* Xt, long long x_rows, const float* Yt, long long y_rows, int M, int P, int slot0,
+                     int B, float* out, cg_stream_t stream) {
+  const long long total = static_cast<long long>(B) * M * P;
+  if (total <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::outer_rows_cl_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(Xt, x_rows, Yt, y_rows, M, P, slot0, B, out);
   CG_LAUNCH_CHECK();
   return 0;
 }

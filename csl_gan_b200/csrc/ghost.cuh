@@ -4,8 +4,8 @@
 //
 // Both Gram matrices are computed on tcgen05 for ns = 128/Q samples at once: the 128 rows of a tile
 // are (sample, q) pairs, the contraction runs over output channels (Xt, NHWC backprops) and over
-// (filter tap, input channel) (Yt, space-to-depth NHWC activations, one 5-D TMA box per tap and
-// 32-channel block).  A tile is BOTH MMA operands (D += T T^T), so one 16 KB TMA load feeds a full
+// (filter tap, input channel) (Yt, space-to-depth channels-last activations, one 5-D TMA box per tap
+// and 32-channel chunk; the same staged tensors the channels-last contraction uses, read K-major here).  A tile is BOTH MMA operands (D += T T^T), so one 16 KB TMA load feeds a full
 // 128x128x32 MMA block -- 4x less operand traffic than the direct contraction -- and the epilogue reads
 // only the Q x Q diagonal blocks.  Cost per sample 2*Q*128*(O + P) FLOP instead of 2*O*P*Q plus an
 // O*P-element epilogue; for the 8x8 and 4x4 layers of the CelebA critic that is 2-4x fewer FLOPs and
@@ -37,6 +37,14 @@ struct GhostParams {
   int n_items;               // ceil(n_slots / ns)
   float* norm2;              // norm2[slot - slot0] += ||G_slot||^2
 };
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                             int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
@@ -86,15 +94,15 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
         for (int kb = 0; kb < n_ob; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kGTileBytes);
-          tma_load_2d(tiles + stage * kGTileBytes, &tmap_xt, &full_bar[stage], kb * 32, s0 * p.Q);
+          tma_load_3d(tiles + stage * kGTileBytes, &tmap_xt, &full_bar[stage], 0, s0 * p.Q, kb);
           if (++stage == kGStages) { stage = 0; phase ^= 1; }
         }
         for (int t = 0; t < n_taps; ++t) {
           for (int cb = 0; cb < n_cb; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], kGTileBytes);
-            tma_load_5d(tiles + stage * kGTileBytes, &tmap_yt, &full_bar[stage], cb * 32, p.tap_woff[t],
-                        p.tap_hoff[t], s0, p.tap_plane[t]);
+            tma_load_5d(tiles + stage * kGTileBytes, &tmap_yt, &full_bar[stage], 0, p.tap_woff[t], p.tap_hoff[t], s0,
+                        p.tap_plane[t] * n_cb + cb);
             if (++stage == kGStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -164,70 +172,6 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kGTmemCols); }
-}
-
-// ------------------------------------------------------------------------------------------
-// staging for the ghost path
-// ------------------------------------------------------------------------------------------
-// src [B][R][Q] -> dst[(slot0+n)*Q + q][r] = tf32(scale*src[n][r][q]); grid (ceil(Q/32), ceil(R/32), B), block (32,8)
-__global__ void stage_nhwc_rows_kernel(const float* __restrict__ src, int R, int Q, float scale,
-                                       float* __restrict__ dst, long long dst_pitch, int slot0) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.z;
-  const int q0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const float* s = src + static_cast<long long>(n) * R * Q;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    const int r = r0 + threadIdx.y + i, q = q0 + threadIdx.x;
-    tile[threadIdx.y + i][threadIdx.x] = (r < R && q < Q) ? scale * s[static_cast<long long>(r) * Q + q] : 0.f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    const int q = q0 + threadIdx.y + i, r = r0 + threadIdx.x;
-    if (q < Q && r < R)
-      dst[(static_cast<long long>(slot0 + n) * Q + q) * dst_pitch + r] = round_tf32(tile[threadIdx.x][threadIdx.y + i]);
-  }
-}
-
-struct S2dParams {
-  int B, C, H, W, Cp;
-  int Hs, Ws, n_rh, n_rw, sh, sw, ah_min, aw_min;
-  int rho_h[CG_MAX_KH], rho_w[CG_MAX_KH];
-  float scale;
-  int slot0;
-  long long slot_stride, plane_stride;     // in floats
-};
-
-// src [B][C][H][W] -> dst[plane=(jh,jw)][slot][hs][ws][c] (channels innermost), zero padded.
-// grid (ceil(C/32), B), block 256, smem 32*(H*W+1) floats.
-__global__ void stage_nhwc_s2d_kernel(const float* __restrict__ src, const __grid_constant__ S2dParams p,
-                                      float* __restrict__ dst) {
-  extern __shared__ float sm[];
-  const int n = blockIdx.y, c0 = blockIdx.x * 32;
-  const int nc = min(32, p.C - c0);
-  const int hw = p.H * p.W, ld = hw + 1;
-  const float* base = src + (static_cast<long long>(n) * p.C + c0) * hw;
-  for (int i = threadIdx.x; i < nc * hw; i += blockDim.x) {
-    const int c = i / hw, r = i - c * hw;
-    sm[c * ld + r] = base[i];
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int per_plane = p.Hs * p.Ws;
-  const int total = p.n_rh * p.n_rw * per_plane;
-  for (int i = warp; i < total; i += nwarps) {
-    const int pl = i / per_plane, rem = i - pl * per_plane;
-    const int hs = rem / p.Ws, ws = rem - hs * p.Ws;
-    const int jh = pl / p.n_rw, jw = pl - jh * p.n_rw;
-    const int h = p.sh * (hs + p.ah_min) + p.rho_h[jh];
-    const int w = p.sw * (ws + p.aw_min) + p.rho_w[jw];
-    float v = 0.f;
-    if (lane < nc && h >= 0 && h < p.H && w >= 0 && w < p.W) v = p.scale * sm[lane * ld + h * p.W + w];
-    if (c0 + lane < p.Cp)
-      dst[pl * p.plane_stride + static_cast<long long>(p.slot0 + n) * p.slot_stride +
-          static_cast<long long>(rem) * p.Cp + c0 + lane] = round_tf32(v);
-  }
 }
 
 }  // namespace cg

@@ -55,6 +55,8 @@ class LayerPlan:
         self.max_passes = 0
         self.use_ghost = True
         self.gplan = None
+        self.force_legacy = False          # tests: exercise the kw-plane (legacy) path on any geometry
+        self.impl = None                   # ClLayerPlan when the channels-last path applies
 
     # ------------------------------------------------------------------ geometry / buffers
     def _setup(self, act: torch.Tensor, Bpad: int, max_passes: int):
@@ -119,12 +121,6 @@ class LayerPlan:
             self.bias_rows = torch.zeros((S, self.bias_len), device=dev) if self.b_idx is not None else None
             if self.kind == "convT" and self.b_idx is not None:
                 self._bias_scratch = torch.empty((self.bias_len, _round_up(Bpad * H * W, 4)), device=dev)
-            # ghost norms (Gram matrices from channels-last staging) when Q = Ho*Wo divides 128
-            self.gplan = L.plan_ghost(self.geom) if self.use_ghost else None
-            if self.gplan is not None:
-                self.Xt = torch.zeros((S * self.Q, _round_up(self.M, 4)), device=dev)
-                n_planes = self.gplan.n_rh * self.gplan.n_rw
-                self.Yt = torch.zeros(n_planes * S * self.gplan.slot_stride, device=dev)
         self.nkb = self.Qpad // KBLK if self.kind != "linear" else 1
         # gradient-natural accumulation buffer T[m][kh][kw*C + c] (Linear: == parameter layout)
         self.T = torch.zeros((self.M, self.KH * self.KW * self.Cn), device=dev)
@@ -133,13 +129,34 @@ class LayerPlan:
     def _ensure(self, act: torch.Tensor, Bpad: int, max_passes: int):
         sig = (tuple(act.shape[1:]), Bpad, max_passes, act.device)
         if not self.ready or sig != self.sig:
-            self._setup(act, Bpad, max_passes)
+            from .cl_plan import ClLayerPlan
+            self.impl = None
+            if self.kind == "linear" and act.dim() != 2:
+                raise NotImplementedError(
+                    f"{self.name}: Linear layers with >2-D inputs are not supported (got {tuple(act.shape)})")
+            g = ClLayerPlan.geometry(self.layer, self.kind, act.shape)
+            if not self.force_legacy and L.cl_supported(g[11], g[12]):
+                self.impl = ClLayerPlan(self.name, self.layer, self.kind, self.w_idx, self.b_idx, self.use_ghost)
+                self.impl.setup(act, Bpad, max_passes)
+                self.Bpad, self.max_passes = Bpad, max_passes
+                self.ready = True
+            else:
+                self._setup(act, Bpad, max_passes)
             self.sig = sig
+
+    @property
+    def path(self) -> str:
+        return "channels_last" if self.impl is not None else "kw_planes"
 
     # ------------------------------------------------------------------ capture
     def capture_activation(self, act: torch.Tensor, pass_idx: int, Bpad: int, max_passes: int):
-        act = L.require_cuda_f32(act.detach(), f"{self.name}: activation")
+        act = act.detach()
+        if not act.is_cuda or act.dtype != torch.float32:
+            L.require_cuda_f32(act, f"{self.name}: activation")
         self._ensure(act, Bpad, max_passes)
+        if self.impl is not None:
+            return self.impl.capture_activation(act, pass_idx)
+        act = act.contiguous()
         B = act.shape[0]
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(act.device)
@@ -149,17 +166,16 @@ class LayerPlan:
         elif self.kind == "conv":
             L.call("cg_stage_unfold", L.ptr(act), B, C.byref(self.geom), C.byref(self.plan), 1.0,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
-            if self.gplan is not None:
-                L.call("cg_stage_nhwc_s2d", L.ptr(act), B, C.byref(self.geom), C.byref(self.gplan), 1.0,
-                       L.ptr(self.Yt), self.S, slot0, st)
         else:  # convT: the activation is the plain operand
             L.call("cg_stage_rows", L.ptr(act), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, 1.0,
                    L.ptr(self.X), self.X.stride(0), slot0, None, st)
-            if self.gplan is not None:
-                L.call("cg_stage_nhwc_rows", L.ptr(act), B, self.M, self.Q, 1.0, L.ptr(self.Xt),
-                       self.Xt.stride(0), slot0, st)
 
     def capture_backprop(self, grad_out: torch.Tensor, pass_idx: int, scale: float):
+        if self.impl is not None:
+            g = grad_out.detach()
+            if not g.is_cuda or g.dtype != torch.float32:
+                L.require_cuda_f32(g, f"{self.name}: backprop")
+            return self.impl.capture_backprop(g, pass_idx, scale)
         g = L.require_cuda_f32(grad_out.detach(), f"{self.name}: backprop")
         B = g.shape[0]
         slot0 = pass_idx * self.Bpad
@@ -171,19 +187,16 @@ class LayerPlan:
             # rowsum is indexed by absolute slot inside the kernel -> pass the buffer base
             L.call("cg_stage_rows", L.ptr(g), B, self.M, self.Q, self.Wo, self.Wop, self.Qpad, scale,
                    L.ptr(self.X), self.X.stride(0), slot0, L.ptr(self.bias_rows), st)
-            if self.gplan is not None:
-                L.call("cg_stage_nhwc_rows", L.ptr(g), B, self.M, self.Q, scale, L.ptr(self.Xt),
-                       self.Xt.stride(0), slot0, st)
         else:
             L.call("cg_stage_unfold", L.ptr(g), B, C.byref(self.geom), C.byref(self.plan), scale,
                    L.ptr(self.Y), self.Y.stride(0), slot0, st)
-            if self.gplan is not None:
-                L.call("cg_stage_nhwc_s2d", L.ptr(g), B, C.byref(self.geom), C.byref(self.gplan), scale,
-                       L.ptr(self.Yt), self.S, slot0, st)
             if self.bias_rows is not None:
                 hw = g.shape[2] * g.shape[3]
                 L.call("cg_stage_rows", L.ptr(g), B, self.bias_len, hw, hw, hw, hw, scale,
                        L.ptr(self._bias_scratch), self._bias_scratch.stride(0), 0, L.ptr(self.bias_rows[slot0:]), st)
+
+    def live_bias_rows(self) -> torch.Tensor:
+        return self.impl.bias_rows if self.impl is not None else self.bias_rows
 
     # ------------------------------------------------------------------ contraction launches
     def _desc(self, X: torch.Tensor) -> L.ContractDesc:
@@ -202,20 +215,14 @@ class LayerPlan:
 
     def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
         """norm2_row[slot] += ||G_slot||_F^2 for the slots of one pass."""
+        if self.impl is not None:
+            return self.impl.weight_norm2(norm2_row, pass_idx, B, n_joint)
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
         if self.kind == "linear":
             if n_joint != 1:
                 raise NotImplementedError("joint (accum_passes=True) norms for Linear layers")
             L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
-            return
-        if self.gplan is not None and n_joint == 1:
-            gd = L.GhostDesc()
-            gd.Xt, gd.xt_pitch, gd.xt_rows = L.ptr(self.Xt), self.Xt.stride(0), self.Xt.shape[0]
-            gd.Yt, gd.n_slots_total, gd.O = L.ptr(self.Yt), self.S, self.M
-            gd.slot0, gd.n_slots = slot0, B
-            gd.norm2, gd.max_ctas = L.ptr(norm2_row[slot0:]), 0
-            L.call("cg_ghost_norm", C.byref(gd), C.byref(self.geom), C.byref(self.gplan), st)
             return
         d = self._desc(self.X)
         d.group_mode, d.n_groups = L.GROUP_SAMPLE, B
@@ -225,6 +232,8 @@ class LayerPlan:
         L.call("cg_contract", C.byref(d), st)
 
     def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int):
+        if self.impl is not None:
+            return self.impl.bias_norm2(norm2_row, pass_idx, B)
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
         if self.kind == "linear":
@@ -236,12 +245,16 @@ class LayerPlan:
 
     def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
         """Xc = tf32(X * factor[slot]) over the slot range (clip factors folded into one operand)."""
+        if self.impl is not None:
+            return self.impl.scale_backprops(factor_row, slot_lo, slot_hi)
         st = L.stream_ptr(factor_row.device)
         L.call("cg_scale_slots", L.ptr(self.X), L.ptr(self.Xc), self.M, self.X.stride(0), self.x_slot_stride,
                slot_lo, slot_hi, L.ptr(factor_row), st)
 
     def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
         """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots."""
+        if self.impl is not None:
+            return self.impl.weighted_sum(out_w, slot_lo, slot_hi, sm_count, accumulate)
         st = L.stream_ptr(out_w.device)
         d = self._desc(self.Xc)
         # mirror of the tile choice in cg_contract (csrc/abi.cu)
@@ -295,6 +308,8 @@ class LayerPlan:
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
                           accumulate: bool):
+        if self.impl is not None:
+            return self.impl.bias_weighted_sum(out_b, factor_row, slot_lo, slot_hi, accumulate)
         st = L.stream_ptr(out_b.device)
         R = self.bias_rows.shape[1]
         L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row), slot_lo, slot_hi, R,
@@ -303,6 +318,8 @@ class LayerPlan:
     def materialize(self, pass_idx: int, B: int) -> torch.Tensor:
         """[B, *weight.shape] per-sample weight gradients of one pass (rare path: reference
         train.py:233, 447 and tests)."""
+        if self.impl is not None:
+            return self.impl.materialize(pass_idx, B)
         slot0 = pass_idx * self.Bpad
         w = self.layer.weight
         out = torch.zeros((B,) + tuple(w.shape), device=w.device)

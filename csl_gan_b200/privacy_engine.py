@@ -529,7 +529,7 @@ class PrivacyEngine:
                 for ps in range(n_passes):
                     B = self._pass_B[ps]
                     lo = ps * self.Bpad
-                    outs.append(plan.bias_rows[lo:lo + B].clone() if (plan, ps) in self._bp_seen
+                    outs.append(plan.live_bias_rows()[lo:lo + B].clone() if (plan, ps) in self._bp_seen
                                 else torch.zeros((B,) + tuple(p.shape), device=self.device))
         g = torch.stack(outs, dim=0)
         if self.accum_passes:

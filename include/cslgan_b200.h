@@ -143,10 +143,11 @@ int cg_outer_rows(const float* X, long long x_pitch, const float* Y, long long y
 /* ---------------------------------------------------------------------------------------------
  * Ghost norms for layers with few window positions (Q = Ho*Wo divides 128):
  *   ||G_n||^2 = sum_{q,q'} (Xn^T Xn)[q,q'] (Un^T Un)[q,q']
- * Both Gram matrices run on tcgen05 for 128/Q samples per tile from channels-last staging:
- *   Xt[(slot*Q + q)][o]                         (cg_stage_nhwc_rows)
- *   Yt[plane(jh,jw)][slot][hs][ws][c]           (cg_stage_nhwc_s2d; space-to-depth so every filter
- *                                                tap is a unit-stride window = one 5-D TMA box)
+ * Both Gram matrices run on tcgen05 for 128/Q samples per tile from the channels-last staging of the
+ * main path (cg_stage_xt / cg_stage_yt, un-merged plan), read here as K-major tiles:
+ *   Xt[o/32][slot*Q + q][o%32]
+ *   Yt[plane*n_cb + c/32][slot][hs][ws][c%32]   (space-to-depth so every filter tap is a unit-stride
+ *                                                window = one 5-D TMA box)
  * Same result as cg_contract(CG_EPI_SUMSQ) (replaces calc_sample_norms, reference train.py:311-314),
  * without the O x P-element epilogue per sample.
  * ------------------------------------------------------------------------------------------- */
@@ -154,22 +155,22 @@ typedef struct cg_ghost_plan {
   int n_rh, n_rw;            /* distinct row / column residues                               */
   int Hs, Ws;                /* staged plane extent                                          */
   int ah_min, aw_min;
-  int Cp;                    /* channels rounded up to 4 (16-byte pitch)                     */
+  int Cp;                    /* staged channels rounded up to 32 (whole 128-byte chunks)     */
   int rho_h[CG_MAX_KH], rho_w[CG_MAX_KH];
   int tap_plane[CG_MAX_KH * CG_MAX_KH], tap_hoff[CG_MAX_KH * CG_MAX_KH], tap_woff[CG_MAX_KH * CG_MAX_KH];
-  long long slot_stride;     /* floats per slot inside a plane = Hs*Ws*Cp                    */
+  long long slot_stride;     /* floats per slot inside one 32-channel chunk = Hs*Ws*32      */
+  int merged;                /* 1: filter columns folded into the channel axis (c' = kw*C + c) for thin
+                                inputs such as the 3-channel image; taps then run over kh only        */
+  int Cs;                    /* staged channels per tap: C, or KW*C when merged                       */
+  int n_taps;                /* KH*KW, or KH when merged                                              */
 } cg_ghost_plan;
+typedef cg_ghost_plan cg_cl_plan;
 
 /* returns non-zero (with a message) when the geometry is outside the ghost path's envelope */
 int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan);
 
-int cg_stage_nhwc_rows(const float* src, int B, int R, int Q, float scale, float* dst, long long dst_pitch,
-                       int slot0, cg_stream_t stream);
-int cg_stage_nhwc_s2d(const float* src, int B, const cg_unfold_geom* g, const cg_ghost_plan* plan, float scale,
-                      float* dst, int n_slots_total, int slot0, cg_stream_t stream);
-
 typedef struct cg_ghost_desc {
-  const float* Xt; long long xt_pitch; long long xt_rows;   /* [n_slots_total*Q][O]        */
+  const float* Xt; long long xt_pitch; long long xt_rows;   /* xt_rows = n_slots_total*Q (xt_pitch unused) */
   const float* Yt; int n_slots_total;                       /* plane-major staged tensor   */
   int O;
   int slot0, n_slots;                                       /* slots to process            */
@@ -178,6 +179,53 @@ typedef struct cg_ghost_desc {
 } cg_ghost_desc;
 
 int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Channels-last contraction (main path).  Same three epilogues and the same operations replaced as
+ * cg_contract (calc_sample_norms / _weighted_sum / materialised grad_sample, reference
+ * train.py:311-314, 399, 233), but both operands are staged channels-innermost with no unfold:
+ *   Xt[m/32][slot*Q + q][m%32]                    cg_stage_xt (element-wise from a channels_last tensor)
+ *   Yt[plane*n_cb + c'/32][slot][hs][ws][c'%32]   cg_stage_yt (space-to-depth; thin inputs fold kw into c')
+ * (32-channel chunks outermost, so one TMA box fetches every chunk of a tile)
+ * and fed to tcgen05 as MN-major operands: a k-block is 32 window positions (Q >= 32), 32/Q samples
+ * (Q < 32, split-K mode) or the Q positions of one sample (8 | Q < 32, per-sample mode).
+ * Linear layers are Q = 1.  CG_EPI_ACCUM writes the gradient-natural layout out[m][tap][c'] (which
+ * is the memory order of a channels_last weight).
+ * ------------------------------------------------------------------------------------------- */
+int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan);
+
+/* src addressed as src[n*sn + m*sm + oh*sh + ow*sw] (any layout; fastest when sm == 1).
+ * Xt[m/32][(slot0+n)*Q + q][m%32] = tf32(scale*src), rows_total = rows of each chunk (n_slots_total*Q);
+ * optional bias_rows[(slot0+n)*M + m] = scale*sum_q src (per-sample bias gradients) and
+ * sumsq[slot0+n] = sum (scale*src)^2 (closed-form Linear norms). */
+int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M,
+                int Ho, int Wo, float scale, float* dst, long long rows_total, int slot0, float* bias_rows,
+                float* sumsq, cg_stream_t stream);
+
+/* src addressed as src[n*sn + c*sc + h*sh + w*sw]; Yt as described above (zero padded). */
+int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
+                const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, float* dst, int n_slots_total,
+                int slot0, cg_stream_t stream);
+
+typedef struct cg_cl_desc {
+  const float* Xt; long long xt_pitch; long long xt_rows; int M;   /* xt_rows = n_slots_total*Q (xt_pitch unused) */
+  const float* Yt; int n_slots_total;
+  int group_mode;              /* CG_GROUP_SAMPLE: one group per slot in [slot_lo, slot_lo+n_groups)
+                                  CG_GROUP_SPLITK: slots [slot_lo, slot_hi) cut into n_groups K ranges */
+  int n_groups;
+  int slot_lo, slot_hi;
+  int epi;
+  float* out;
+  long long out_group_stride;
+  int max_ctas;
+} cg_cl_desc;
+
+int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream);
+
+/* out[n][m][p] = Xt[m/32][slot0+n][m%32] * Yt[p/32][slot0+n][p%32]  (materialised Linear per-sample
+ * gradients; x_rows / y_rows = rows of each chunk) */
+int cg_outer_rows_cl(const float* Xt, long long x_rows, const float* Yt, long long y_rows, int M, int P,
+                     int slot0, int B, float* out, cg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Small reductions around the contraction

@@ -10,7 +10,7 @@ hdr, data = rows[hi], rows[hi + 1:]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 seq = [(r[ki], float(r[vi].replace(",", ""))) for r in data if len(r) > vi]
 short = lambda n: n.split("(")[0].split("::")[-1][:40]
-idx = [i for i, (n, _) in enumerate(seq) if "stage_unfold" in n]
+idx = [i for i, (n, _) in enumerate(seq) if "stage_unfold" in n or "stage_yt" in n]
 per_step = 8
 start = idx[per_step] if len(idx) > per_step else idx[0]
 end = idx[2 * per_step] if len(idx) > 2 * per_step else len(seq)

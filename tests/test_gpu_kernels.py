@@ -101,16 +101,26 @@ def _conv_case(B, Cin, Cout, H, W, k, s, p, d=1, seed=0):
     (2, 4, 6, 13, 12, 3, 2, 0, 2),       # dilation 2, no padding
     (2, 3, 5, 10, 10, 4, 3, 1, 1),       # stride 3, even kernel
 ])
-def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d):
-    """stage_unfold + stage_rows + cg_contract (all three epilogues) vs the oracle's unfold/einsum."""
+@pytest.mark.parametrize("path", ["channels_last", "channels_last_from_cl_tensors", "kw_planes"])
+def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d, path):
+    """staging + contraction (all three epilogues) vs the oracle's unfold/einsum, on both operand paths:
+    channels-last MN-major (main) and kw-plane K-major (geometries the main path cannot tile)."""
     from csl_gan_b200.grad_sample import LayerPlan
     conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p, d)
+    if path != "kw_planes" and not L.cl_supported(Ho, Wo):
+        pytest.skip("window grid not tileable by the channels-last path")
     gw_ref, gb_ref = O.conv2d_grad_sample(conv, A, Bp)                # [B, Cout, Cin, k, k], [B, Cout]
     conv = conv.to(DEV)
     plan = LayerPlan("conv", conv, 0, 1)
+    plan.force_legacy = path == "kw_planes"
+    plan.use_ghost = False
     Bpad = 32
-    plan.capture_activation(A.to(DEV), 0, Bpad, 1)
-    plan.capture_backprop(Bp.to(DEV), 0, 1.0)
+    Ag, Bg = A.to(DEV), Bp.to(DEV)
+    if path == "channels_last_from_cl_tensors":
+        Ag, Bg = Ag.contiguous(memory_format=torch.channels_last), Bg.contiguous(memory_format=torch.channels_last)
+    plan.capture_activation(Ag, 0, Bpad, 1)
+    plan.capture_backprop(Bg, 0, 1.0)
+    assert plan.path == ("kw_planes" if path == "kw_planes" else "channels_last")
     # STORE
     gs = plan.materialize(0, B).cpu()
     scale = gw_ref.abs().max().item()
@@ -119,7 +129,7 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d)
         rel = (gs[n] - gw_ref[n]).norm() / gw_ref[n].norm()
         assert rel < 1e-3, (n, rel)
     # bias rows
-    np.testing.assert_allclose(plan.bias_rows[:B].cpu().numpy(), gb_ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(plan.live_bias_rows()[:B].cpu().numpy(), gb_ref.numpy(), rtol=1e-4, atol=1e-4)
     # SUMSQ
     norm2 = torch.zeros(Bpad, device=DEV)
     plan.weight_norm2(norm2, 0, B)
@@ -155,7 +165,7 @@ def test_ghost_norms_match_direct_and_oracle(B, Cin, Cout, H, W, k, s, p):
         plan.use_ghost = ghost
         plan.capture_activation(A.to(DEV), 1, 32, 2)          # second pass: exercises slot offsets
         plan.capture_backprop(Bp.to(DEV), 1, 1.0)
-        assert (plan.gplan is not None) == ghost
+        assert plan.path == "channels_last" and plan.impl.ghost == ghost
         norm2 = torch.zeros(64, device=DEV)
         plan.weight_norm2(norm2, 1, B)
         torch.cuda.synchronize()
@@ -184,10 +194,29 @@ def test_conv_transpose_per_sample_grads():
     plan = LayerPlan("convT", ct, 0, 1)
     plan.capture_activation(A.to(DEV), 0, 32, 1)
     plan.capture_backprop(Bp.to(DEV), 0, 1.0)
+    assert plan.path == "kw_planes"                       # 7x5 window grid: not tileable by the main path
     gs = plan.materialize(0, B).cpu()
     for n in range(B):
         assert ((gs[n] - gw_ref[n]).norm() / gw_ref[n].norm()).item() < 1e-3
-    np.testing.assert_allclose(plan.bias_rows[:B].cpu().numpy(), gb_ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(plan.live_bias_rows()[:B].cpu().numpy(), gb_ref.numpy(), rtol=1e-4, atol=1e-4)
+    # a tileable geometry goes through the channels-last path (8x8 inputs, roles of the operands swapped)
+    ct2 = torch.nn.ConvTranspose2d(6, 4, 4, stride=2, padding=1)
+    A2 = torch.randn(B, 6, 8, 8, generator=g)
+    Bp2 = torch.randn(ct2(A2).shape, generator=g)
+    gw2, gb2 = O.conv_transpose2d_grad_sample(ct2, A2, Bp2)
+    ct2 = ct2.to(DEV)
+    plan2 = LayerPlan("convT", ct2, 0, 1)
+    plan2.use_ghost = False
+    plan2.capture_activation(A2.to(DEV), 0, 32, 1)
+    plan2.capture_backprop(Bp2.to(DEV), 0, 1.0)
+    assert plan2.path == "channels_last"
+    gs2 = plan2.materialize(0, B).cpu()
+    for n in range(B):
+        assert ((gs2[n] - gw2[n]).norm() / gw2[n].norm()).item() < 1e-3
+    np.testing.assert_allclose(plan2.live_bias_rows()[:B].cpu().numpy(), gb2.numpy(), rtol=1e-4, atol=1e-4)
+    n2 = torch.zeros(32, device=DEV)
+    plan2.weight_norm2(n2, 0, B)
+    np.testing.assert_allclose(n2[:B].cpu().double().numpy(), gw2.reshape(B, -1).double().pow(2).sum(1).numpy(), rtol=2e-3)
 
 
 @pytest.mark.parametrize("B,P,Od", [(600, 794, 128), (37, 128, 10), (5, 128, 1), (64, 8192, 1)])
