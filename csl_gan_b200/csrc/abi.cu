@@ -691,10 +691,11 @@ int cg_weighted_colsum(const float* rows_in, const float* factor, int slot_lo, i
   if (R <= 0) return 0;
   if (!accumulate) CG_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * R, S(stream)));
   if (slot_hi <= slot_lo) return 0;
-  int ny = (slot_hi - slot_lo + 63) / 64;
-  if (ny > 64) ny = 64;
-  dim3 grid((R + 127) / 128, ny);
-  cg::weighted_colsum_kernel<<<grid, 128, 0, S(stream)>>>(rows_in, factor, slot_lo, slot_hi, R, out);
+  int ny = (slot_hi - slot_lo + 31) / 32;             // >= 32 slots per block
+  if (ny > 128) ny = 128;
+  if (ny < 1) ny = 1;
+  dim3 grid((R + 31) / 32, ny), block(32, 8);
+  cg::weighted_colsum_kernel<<<grid, block, 0, S(stream)>>>(rows_in, factor, slot_lo, slot_hi, R, out);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -327,17 +327,25 @@ __global__ void permute_accum_kernel(const float* __restrict__ T, float* __restr
   }
 }
 
-// out[r] (+)= sum_slot factor[slot] * rows_in[slot*R + r]; one thread per r, slots split over blockIdx.y
+// out[r] (+)= sum_slot factor[slot] * rows_in[slot*R + r].  block (32 columns, 8 slot lanes); slots are also
+// split over blockIdx.y so the (tiny) reduction is spread over many SMs; one atomic per column per block.
 __global__ void weighted_colsum_kernel(const float* __restrict__ rows_in, const float* __restrict__ factor,
                                        int slot_lo, int slot_hi, int R, float* __restrict__ out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
+  __shared__ float red[8][33];
+  const int r = blockIdx.x * 32 + threadIdx.x;
   const int per = (slot_hi - slot_lo + gridDim.y - 1) / gridDim.y;
   const int lo = slot_lo + blockIdx.y * per;
   const int hi = min(lo + per, slot_hi);
   float acc = 0.f;
-  for (int s = lo; s < hi; ++s) acc = fmaf(factor[s], rows_in[static_cast<long long>(s) * R + r], acc);
-  if (hi > lo) atomicAdd(out + r, acc);
+  if (r < R)
+    for (int s = lo + threadIdx.y; s < hi; s += 8) acc = fmaf(__ldg(factor + s), __ldg(rows_in + static_cast<long long>(s) * R + r), acc);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && r < R) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc += red[k][threadIdx.x];
+    if (hi > lo) atomicAdd(out + r, acc);
+  }
 }
 
 __global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int n_slots, int slot_lo, int slot_hi,

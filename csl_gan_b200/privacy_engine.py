@@ -448,16 +448,18 @@ class PrivacyEngine:
         self._norm2.zero_()
         joint = 1
         for plan in self._plans:
-            passes = range(1) if self.accum_passes else range(self._pass_count.get(plan, 0))
-            for ps in passes:
-                if not self.accum_passes and (plan, ps) not in self._bp_seen:
-                    continue                       # layer got no backprop in this pass -> zero gradient
-                B = self._pass_B[ps]
-                plan.weight_norm2(self._norm2[plan.w_idx], ps, B, joint)
+            live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
+            if not live:
+                continue                           # layer got no backprop at all -> zero gradient
+            # when every pass fills its slots exactly, the passes are one contiguous slot range: one launch
+            if len(live) == n_passes and all(self._pass_B[ps] == self.Bpad for ps in live):
+                spans = [(0, n_passes * self.Bpad)]
+            else:
+                spans = [(ps, self._pass_B[ps]) for ps in live]
+            for ps, nb in spans:
+                plan.weight_norm2(self._norm2[plan.w_idx], ps, nb, joint)
                 if plan.b_idx is not None:
-                    if joint != 1:
-                        raise NotImplementedError("accum_passes=True bias norms")
-                    plan.bias_norm2(self._norm2[plan.b_idx], ps, B)
+                    plan.bias_norm2(self._norm2[plan.b_idx], ps, nb)
         self._norms_valid = True
         self._factors_valid = False
 
