@@ -7,7 +7,9 @@ import csl_gan_b200 as cg
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 dev = torch.device("cuda", 0)
+torch.backends.cudnn.benchmark = True
 D, real_h, fake_h, y, cfg = bench.make_workload("celeba_d64_gc", B, dev)
+D = D.to(memory_format=torch.channels_last)
 real_pin, fake_pin = real_h.pin_memory(), fake_h.pin_memory()
 opt = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9))
 eng = cg.PrivacyEngine(D, batch_size=B, sample_size=180000, noise_multiplier=0.5, max_grad_norm=cfg["C"],
@@ -26,7 +28,7 @@ def step(hooks=True, collect=None):
     of, _ = D(f); orr, _ = D(r)
     loss = D.real_loss(orr) + D.fake_loss(of)
     marks.append(("forward(+act staging)", ev()))
-    loss.backward()
+    (eng.backward(loss) if hooks else loss.backward())
     marks.append(("backward(+bp staging)", ev()))
     eng.disable_hooks()
     if hooks:
