@@ -11,6 +11,8 @@ from .privacy_engine import PrivacyEngine, calc_sample_norms, GradSampleView  # 
 from .is_engine import ISPrivacyEngine  # noqa: F401
 from .functional import (calc_penalty, calc_WGAN_GP_penalty, calc_lipschitz_penalty_WRT, l2_clip,  # noqa: F401
                          row_l2_norm, vec_max)
+from .backprop_clip import BackpropClipper  # noqa: F401
+from .mean_sampler import DeviceMeanSampler  # noqa: F401
 from . import discriminators, accountant  # noqa: F401
 
 __version__ = "0.1.0"

@@ -158,3 +158,45 @@ def test_rel_lazy_grad_sample_shapes_do_not_need_a_gpu():
             return 2
     v = cg.GradSampleView(FakeEngine(), 0)
     assert v.size(1) == 7 and tuple(v.shape) == (2, 7, 3, 4) and len(v) == 2 and v.dim() == 4
+
+
+def test_backprop_clipper_bounds_bookkeeping():
+    """grad_l2_bounds as reference backprop_clip.py:71-96 derives them (shapes from a dry forward)."""
+    import math
+    from csl_gan_b200.backprop_clip import BackpropClipper
+    torch.manual_seed(0)
+    D = cg.discriminators.MNISTVanillaD(n_classes=0)
+    # explicit parameters: Linear weight bound = C_in * C_back, bias bound = C_back
+    bc = BackpropClipper(D, [0.01, 0.02], [20, 5], wrap=False)
+    assert bc.grad_l2_bounds == pytest.approx([20 * 0.01, 0.01, 5 * 0.02, 0.02])
+    # automatic parameters (reference :62-80)
+    bc = BackpropClipper(D, None, None, auto_activation_scale=0.2, auto_weight_grad_scale=1e-3, wrap=False)
+    c_in1 = math.sqrt(784 * 0.2 ** 2)
+    w1 = math.sqrt(128 * 784 * 1e-3 ** 2)
+    assert bc.input_clip_params[0] == pytest.approx(c_in1)
+    assert bc.grad_l2_bounds[0] == pytest.approx(w1) and bc.grad_l2_bounds[1] == pytest.approx(w1 / c_in1)
+    # conv critic: weight bound = C_in * sqrt(out pixels) * C_back, bias bound = C_back * out pixels
+    # (the reference takes prod(out_shape[1:]) of a batch-stripped shape, i.e. H*W, backprop_clip.py:79-93)
+    Dc = cg.discriminators.MNIST_DCRN_D(n_classes=0)
+    bc = BackpropClipper(Dc, [0.01] * 3, [20] * 3, wrap=False)
+    n1 = 14 * 14
+    assert bc.grad_l2_bounds[0] == pytest.approx(20 * math.sqrt(n1) * 0.01) and bc.grad_l2_bounds[1] == pytest.approx(0.01 * n1)
+    assert len(bc.grad_l2_bounds) == 5
+
+
+def test_device_mean_sampler_shapes_and_privacy_cost():
+    from csl_gan_b200.mean_sampler import DeviceMeanSampler
+    g = torch.Generator().manual_seed(0)
+    ms = DeviceMeanSampler(torch.rand(2, 5, 3, 8, 8, generator=g), noise_std=0.12, mean_size=1000, dataset_size=180000,
+                           smallest_class_size=70000, generator=g)
+    x, y = ms.sample(12)
+    assert tuple(x.shape) == (12, 3, 8, 8) and tuple(y.shape) == (12,)
+    lab = torch.tensor([1, 0, 1])
+    x2, y2 = ms.sample(3, noise_std=0, noise_mean_std=0, requested_labels=lab)
+    assert torch.equal(y2, lab)
+    for i in range(3):        # with the noise off a sample IS one of the stored class means
+        assert any(torch.equal(x2[i], ms.mean_samples[lab[i], k]) for k in range(5))
+    eps, alpha = ms.get_privacy_cost(1e-6)
+    assert eps > 0
+    one = DeviceMeanSampler(torch.rand(1, 4, 1, 8, 8), 0.2, 100, 1000)
+    assert one.sample(9)[1] is None

@@ -392,6 +392,48 @@ def test_engine_backward_skips_weight_grads_and_handles_channels_last():
             assert rel(p.grad, g) < REL_TOL
 
 
+def test_backprop_clipper_matches_pure_torch_restatement():
+    """Wrapped critic (CUDA l2_clip in forward and on grad-inputs) vs the same clipping written with the
+    oracle's l2_clip (reference backprop_clip.py:18-22, 98-103)."""
+    from csl_gan_b200.backprop_clip import BackpropClipper
+    torch.manual_seed(1)
+    D = DD.MNIST_DCRN_D(n_classes=0).to(DEV)
+    Dref = copy.deepcopy(D)
+    x = torch.randn(6, 1, 28, 28, device=DEV) * 3
+    back, fwd = [0.05, 0.02, 0.5], [5.0, 30.0, 10.0]
+    bc = BackpropClipper(D, back, fwd, device=DEV, input_size=(1, 1, 28, 28))
+    out = D(x)[0]
+    out.sum().backward()
+
+    # restatement: clip inputs forward, clip the gradient flowing out of each layer's input backward
+    class ClipGrad(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t, c):
+            ctx.c = c
+            return t.view_as(t)
+
+        @staticmethod
+        def backward(ctx, g):
+            return O.l2_clip(g, ctx.c), None
+
+    h = x
+    layers = list(Dref.blocks) + [Dref.linOut]
+    for i, layer in enumerate(layers):
+        if i == len(layers) - 1:
+            h = h.reshape(h.size(0), -1)
+        # the reference wraps the LAYER: clip(x) -> layer -> dummy whose grad_input (= grad wrt layer output) is clipped
+        h = ClipGrad.apply(layer(O.l2_clip(h, fwd[i])), back[i])
+        if i < len(layers) - 1:
+            h = torch.nn.functional.leaky_relu(h, 0.2)
+    h.sum().backward()
+    assert rel(out, h) < 1e-5
+    for (n, p), q in zip(D.named_parameters(), Dref.parameters()):
+        assert rel(p.grad, q.grad) < 2e-3, n          # cuDNN TF32-off vs itself: same library, tiny differences
+    bc.disable_hooks()
+    D.zero_grad()
+    D(x)[0].sum().backward()                          # hooks off: only the forward clip remains
+
+
 def test_engine_rejects_cpu_module_and_batchnorm():
     D, *_ = make("mnist_uncond")
     with pytest.raises(cg.CslGanCudaError):
