@@ -49,7 +49,8 @@ class ClDesc(C.Structure):
     _fields_ = [("Xt", C.c_void_p), ("xt_pitch", C.c_longlong), ("xt_rows", C.c_longlong), ("M", C.c_int),
                 ("Yt", C.c_void_p), ("n_slots_total", C.c_int),
                 ("group_mode", C.c_int), ("n_groups", C.c_int), ("slot_lo", C.c_int), ("slot_hi", C.c_int),
-                ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong), ("max_ctas", C.c_int)]
+                ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong), ("max_ctas", C.c_int),
+                ("n_seg", C.c_int), ("seg_stride", C.c_int)]
 
 
 class GhostDesc(C.Structure):
@@ -95,12 +96,16 @@ _PROTOS = {
                               C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p]),
     "cg_cl_contract": (C.c_int, [C.POINTER(ClDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
+    "cg_rowpair_dot": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p]),
+    "cg_joint_rows_sumsq": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cg_outer_rows_cl": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
     "cg_outer_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]),
     "cg_row_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
     "cg_vec_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "cg_vec_fma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cg_clip_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "cg_scale_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,

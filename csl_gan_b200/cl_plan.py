@@ -157,12 +157,28 @@ class ClLayerPlan:
     def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
-        if n_joint != 1:
-            raise NotImplementedError("joint (accum_passes=True) norms")
         if self.kind == "linear":
-            L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
+            if n_joint == 1:
+                L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
+                return
+            # ||sum_p b_p a_p^T||_F^2 = sum_{p,p'} (a_p . a_p') (b_p . b_p')
+            if not hasattr(self, "_ta"):
+                self._ta = torch.empty(self.Bpad, device=norm2_row.device)
+                self._tb = torch.empty(self.Bpad, device=norm2_row.device)
+            out = norm2_row[slot0:]
+            out[:B].zero_()
+            for p1 in range(n_joint):
+                for p2 in range(p1, n_joint):
+                    s1, s2 = slot0 + p1 * self.Bpad, slot0 + p2 * self.Bpad
+                    if p1 == p2:
+                        a, b, w = self.asq[s1:], self.bsq[s1:], 1.0
+                    else:
+                        L.call("cg_rowpair_dot", L.ptr(self.Yt), self.S, self.n_cb, s1, s2, B, L.ptr(self._ta), 0, st)
+                        L.call("cg_rowpair_dot", L.ptr(self.Xt), self.x_rows, self.x_chunks, s1, s2, B, L.ptr(self._tb), 0, st)
+                        a, b, w = self._ta, self._tb, 2.0
+                    L.call("cg_vec_fma", L.ptr(a), L.ptr(b), w, L.ptr(out), B, st)
             return
-        if self.ghost:
+        if self.ghost and n_joint == 1:
             gd = L.GhostDesc()
             gd.Xt, gd.xt_pitch, gd.xt_rows = L.ptr(self.Xt), 32, self.x_rows
             gd.Yt, gd.n_slots_total, gd.O = L.ptr(self.Yt), self.S, self.M
@@ -172,22 +188,29 @@ class ClLayerPlan:
             return
         d = self._desc(self.Xt)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
+        d.n_seg, d.seg_stride = n_joint, self.Bpad
         d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
         L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
 
-    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int):
+    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
+        if n_joint > 1:
+            R = self.bias_rows.shape[1]
+            L.call("cg_joint_rows_sumsq", L.ptr(self.bias_rows), R, slot0, self.Bpad, n_joint, B,
+                   L.ptr(norm2_row[slot0:]), st)
+            return
         if self.kind == "linear":
             norm2_row[slot0:slot0 + B].copy_(self.bsq[slot0:slot0 + B])
             return
         R = self.bias_rows.shape[1]
         L.call("cg_row_sumsq", L.ptr(self.bias_rows[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
 
-    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
-        """Xc = tf32(Xt * factor[slot]): every chunk of Xt is a row of slot-sized (Q*32) segments."""
+    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0):
+        """Xc = tf32(Xt * factor[slot - factor_shift]): every chunk of Xt is a row of slot-sized (Q*32) segments.
+        factor_shift != 0 reuses pass 0's (joint) factors for a later pass."""
         L.call("cg_scale_slots", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * 32, self.Q * 32,
-               slot_lo, slot_hi, L.ptr(factor_row), L.stream_ptr(factor_row.device))
+               slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, L.stream_ptr(factor_row.device))
 
     def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
         st = L.stream_ptr(out_w.device)
@@ -234,9 +257,9 @@ class ClLayerPlan:
                 out_w.add_(dst) if accumulate else out_w.copy_(dst)
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
-                          accumulate: bool):
+                          accumulate: bool, factor_shift: int = 0):
         R = self.bias_rows.shape[1]
-        L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row), slot_lo, slot_hi, R,
+        L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row) - 4 * factor_shift, slot_lo, slot_hi, R,
                L.ptr(out_b), 1 if accumulate else 0, L.stream_ptr(out_b.device))
 
     def materialize(self, pass_idx: int, B: int) -> torch.Tensor:

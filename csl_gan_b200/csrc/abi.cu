@@ -546,6 +546,8 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   p.Q = Q; p.Wo = g->Wo; p.kb_rows = kb_rows; p.kb_s = kb_s;
   p.nkb_slot = (Q >= 32) ? Q / 32 : 1;
   p.group_mode = d->group_mode; p.n_groups = d->n_groups; p.slot_lo = d->slot_lo;
+  p.n_seg = d->n_seg > 0 ? d->n_seg : 1;
+  p.seg_stride = d->seg_stride;
   if (d->group_mode == CG_GROUP_SPLITK) {
     if (d->slot_hi <= d->slot_lo) return 0;
     if (kb_s > 1) {
@@ -598,6 +600,22 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   return 0;
 }
 
+int cg_rowpair_dot(const float* T, long long rows_total, int n_chunks, int row_a, int row_b, int B, float* out,
+                   int accumulate, cg_stream_t stream) {
+  if (B <= 0) return 0;
+  cg::rowpair_dot_kernel<<<(B + 7) / 8, 256, 0, S(stream)>>>(T, rows_total, n_chunks, row_a, row_b, B, out, accumulate);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_joint_rows_sumsq(const float* rows_in, int R, int slot_lo, int seg_stride, int n_seg, int B, float* out,
+                        cg_stream_t stream) {
+  if (B <= 0) return 0;
+  cg::joint_rows_sumsq_kernel<<<(B + 7) / 8, 256, 0, S(stream)>>>(rows_in, R, slot_lo, seg_stride, n_seg, B, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
 int cg_outer_rows_cl(const float* Xt, long long x_rows, const float* Yt, long long y_rows, int M, int P, int slot0,
                      int B, float* out, cg_stream_t stream) {
   const long long total = static_cast<long long>(B) * M * P;
@@ -642,6 +660,15 @@ int cg_vec_mul(const float* a, const float* b, float* out, long long n, cg_strea
   DevInfo d;
   if (dev_info(&d)) return 1;
   cg::vec_mul_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(a, b, out, n);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_vec_fma(const float* a, const float* b, float w, float* out, long long n, cg_stream_t stream) {
+  if (n <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::vec_fma_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(a, b, w, out, n);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -55,6 +55,8 @@ struct ClParams {
   int nkb_slot;                // k-blocks per slot (Q/32 when Q >= 32, else 1)
   int group_mode, n_groups;    // CG_GROUP_SAMPLE: group g = slot slot_lo+g ; CG_GROUP_SPLITK: units [u_lo + g*upg, ..)
   int slot_lo;
+  int n_seg, seg_stride;       // CG_GROUP_SAMPLE: a group also covers slots slot_lo+g + s*seg_stride, s < n_seg
+                               // (per-sample sum over passes: joint clipping of fake_i + real_i)
   long long u_lo, u_hi, upg;   // global k-block units
   int epi;
   float* out;
@@ -65,7 +67,9 @@ struct ClParams {
 
 struct ClItem {
   int mt, nt, g;
-  long long u0, u1;
+  long long u0, u1;            // k-block units of the first segment
+  int n_seg;
+  long long seg_units;         // unit distance between segments
   int tap0, ntap, cb0, ncb;    // the tile's taps [tap0, tap0+ntap) and chunks [cb0, cb0+ncb) of each
 };
 
@@ -86,9 +90,13 @@ __device__ __forceinline__ ClItem cl_decode(const ClParams& p, long long item) {
     c.cb0 = 0;
     c.ncb = p.n_cb;
   }
+  c.n_seg = 1;
+  c.seg_units = 0;
   if (p.group_mode == CG_GROUP_SAMPLE) {
     c.u0 = static_cast<long long>(p.slot_lo + c.g) * p.nkb_slot;
     c.u1 = c.u0 + p.nkb_slot;
+    c.n_seg = p.n_seg;
+    c.seg_units = static_cast<long long>(p.seg_stride) * p.nkb_slot;
   } else {
     c.u0 = p.u_lo + c.g * p.upg;
     c.u1 = c.u0 + p.upg;
@@ -162,7 +170,8 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
           my_hoff = p.tap_hoff[tap];
           my_woff = p.tap_woff[tap];
         }
-        for (long long u = c.u0; u < c.u1; ++u) {
+        for (int sg = 0; sg < c.n_seg; ++sg)
+        for (long long u = c.u0 + sg * c.seg_units; u < c.u1 + sg * c.seg_units; ++u) {
           int slot, q0;
           if (p.kb_s > 1) { slot = static_cast<int>(u) * p.kb_s; q0 = 0; }
           else { slot = static_cast<int>(u / p.nkb_slot); q0 = static_cast<int>(u - static_cast<long long>(slot) * p.nkb_slot) * p.kb_rows; }
@@ -197,7 +206,8 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
         bool first = true;
-        for (long long u = c.u0; u < c.u1; ++u) {
+        const long long n_it = (c.u1 - c.u0) * c.n_seg;
+        for (long long it = 0; it < n_it; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t xs = smem_u32(tiles + stage * kClStageBytes);

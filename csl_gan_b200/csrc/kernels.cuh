@@ -251,11 +251,50 @@ __global__ void outer_rows_kernel(const float* __restrict__ X, long long x_pitch
   }
 }
 
+// out[n] (+)= <T[:, row_a+n, :], T[:, row_b+n, :]> over a chunk-major matrix T[n_chunks][rows_total][32]
+// (cross terms of the joint Linear norm: ||b1 a1^T + b2 a2^T||^2 = ... + 2 (a1.a2)(b1.b2)); one warp per n
+__global__ void rowpair_dot_kernel(const float* __restrict__ T, long long rows_total, int n_chunks, int row_a,
+                                   int row_b, int B, float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= B) return;
+  float acc = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const float* base = T + static_cast<long long>(c) * rows_total * 32;
+    acc = fmaf(base[static_cast<long long>(row_a + n) * 32 + lane], base[static_cast<long long>(row_b + n) * 32 + lane], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[n] = accumulate ? out[n] + acc : acc;
+}
+
+// out[n] = || sum_s rows_in[(slot_lo + n + s*seg_stride)][:] ||^2   (joint per-sample bias-gradient norms)
+__global__ void joint_rows_sumsq_kernel(const float* __restrict__ rows_in, int R, int slot_lo, int seg_stride,
+                                        int n_seg, int B, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= B) return;
+  float acc = 0.f;
+  for (int r = lane; r < R; r += 32) {
+    float v = 0.f;
+    for (int s = 0; s < n_seg; ++s) v += rows_in[static_cast<long long>(slot_lo + n + s * seg_stride) * R + r];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[n] = acc;
+}
+
 __global__ void vec_mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = a[i] * b[i];
+}
+
+__global__ void vec_fma_kernel(const float* __restrict__ a, const float* __restrict__ b, float w, float* __restrict__ out,
+                               long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = fmaf(w * a[i], b[i], out[i]);
 }
 
 __global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_params, int n_slots, int per_layer,

@@ -231,11 +231,16 @@ class LayerPlan:
         d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
         L.call("cg_contract", C.byref(d), st)
 
-    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int):
+    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
         if self.impl is not None:
-            return self.impl.bias_norm2(norm2_row, pass_idx, B)
+            return self.impl.bias_norm2(norm2_row, pass_idx, B, n_joint)
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
+        if n_joint > 1:
+            R = self.bias_rows.shape[1]
+            L.call("cg_joint_rows_sumsq", L.ptr(self.bias_rows), R, slot0, self.Bpad, n_joint, B,
+                   L.ptr(norm2_row[slot0:]), st)
+            return
         if self.kind == "linear":
             # per-sample bias gradient of a Linear layer is the (scaled) backprop itself
             norm2_row[slot0:slot0 + B].copy_(self.bsq[slot0:slot0 + B])
@@ -243,13 +248,13 @@ class LayerPlan:
         R = self.bias_rows.shape[1]
         L.call("cg_row_sumsq", L.ptr(self.bias_rows[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
 
-    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
-        """Xc = tf32(X * factor[slot]) over the slot range (clip factors folded into one operand)."""
+    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0):
+        """Xc = tf32(X * factor[slot - factor_shift]) over the slot range (clip factors folded into one operand)."""
         if self.impl is not None:
-            return self.impl.scale_backprops(factor_row, slot_lo, slot_hi)
+            return self.impl.scale_backprops(factor_row, slot_lo, slot_hi, factor_shift)
         st = L.stream_ptr(factor_row.device)
         L.call("cg_scale_slots", L.ptr(self.X), L.ptr(self.Xc), self.M, self.X.stride(0), self.x_slot_stride,
-               slot_lo, slot_hi, L.ptr(factor_row), st)
+               slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, st)
 
     def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
         """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots."""
@@ -307,12 +312,12 @@ class LayerPlan:
                    1 if accumulate else 0, st)
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
-                          accumulate: bool):
+                          accumulate: bool, factor_shift: int = 0):
         if self.impl is not None:
-            return self.impl.bias_weighted_sum(out_b, factor_row, slot_lo, slot_hi, accumulate)
+            return self.impl.bias_weighted_sum(out_b, factor_row, slot_lo, slot_hi, accumulate, factor_shift)
         st = L.stream_ptr(out_b.device)
         R = self.bias_rows.shape[1]
-        L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row), slot_lo, slot_hi, R,
+        L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row) - 4 * factor_shift, slot_lo, slot_hi, R,
                L.ptr(out_b), 1 if accumulate else 0, st)
 
     def materialize(self, pass_idx: int, B: int) -> torch.Tensor:

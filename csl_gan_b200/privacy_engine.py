@@ -441,23 +441,30 @@ class PrivacyEngine:
         if self._norms_valid:
             return
         n_passes = self._check_captured()
-        if self.accum_passes and n_passes > 1:
-            raise NotImplementedError(
-                "accum_passes=True (joint clipping of fake_i + real_i, -gcs False) is not implemented yet; "
-                "use the reference default grad_clip_split=True")
         self._norm2.zero_()
-        joint = 1
+        joint = n_passes if (self.accum_passes and n_passes > 1) else 1
+        if joint > 1 and len({self._pass_B[ps] for ps in range(n_passes)}) != 1:
+            raise RuntimeError("accum_passes=True needs the same batch size in every pass")
         for plan in self._plans:
             live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
             if not live:
                 continue                           # layer got no backprop at all -> zero gradient
+            if joint > 1:
+                # U2: the per-sample gradients of all passes are summed first; the joint norms live in
+                # pass 0's slots.  A layer missing a backprop in some pass is not supported here.
+                if len(live) != n_passes:
+                    raise NotImplementedError(f"{plan.name}: accum_passes=True with a layer unused in one pass")
+                plan.weight_norm2(self._norm2[plan.w_idx], 0, self._pass_B[0], joint)
+                if plan.b_idx is not None:
+                    plan.bias_norm2(self._norm2[plan.b_idx], 0, self._pass_B[0], joint)
+                continue
             # when every pass fills its slots exactly, the passes are one contiguous slot range: one launch
             if len(live) == n_passes and all(self._pass_B[ps] == self.Bpad for ps in live):
                 spans = [(0, n_passes * self.Bpad)]
             else:
                 spans = [(ps, self._pass_B[ps]) for ps in live]
             for ps, nb in spans:
-                plan.weight_norm2(self._norm2[plan.w_idx], ps, nb, joint)
+                plan.weight_norm2(self._norm2[plan.w_idx], ps, nb, 1)
                 if plan.b_idx is not None:
                     plan.bias_norm2(self._norm2[plan.b_idx], ps, nb)
         self._norms_valid = True
@@ -553,17 +560,27 @@ class PrivacyEngine:
                 if plan.b_idx is not None:
                     outs[plan.b_idx].zero_()
                 continue
-            if len(live) == n_passes:
-                ranges = [(0, slot_hi)]
+            joint = self.accum_passes and n_passes > 1
+            if joint:
+                # every pass is scaled with pass 0's (joint) factors
+                ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], ps * self.Bpad) for ps in live]
+            elif len(live) == n_passes:
+                ranges = [(0, slot_hi, 0)]
             else:
-                ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps]) for ps in live]
+                ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], 0) for ps in live]
             frow_w = self._factors[plan.w_idx if self._per_layer else 0]
-            for i, (lo, hi) in enumerate(ranges):
-                plan.scale_backprops(frow_w, lo, hi)
-                plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0)
-                if plan.b_idx is not None:
-                    frow_b = self._factors[plan.b_idx if self._per_layer else 0]
-                    plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=i > 0)
+            for lo, hi, shift in ranges:
+                plan.scale_backprops(frow_w, lo, hi, shift)
+            if joint or len(ranges) == 1:
+                # the scaled operand now covers every live slot: ONE GEMM over the whole range
+                plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False)
+            else:
+                for i, (lo, hi, _) in enumerate(ranges):
+                    plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0)
+            if plan.b_idx is not None:
+                frow_b = self._factors[plan.b_idx if self._per_layer else 0]
+                for i, (lo, hi, shift) in enumerate(ranges):
+                    plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=i > 0, factor_shift=shift)
         self._clipped = outs
         return outs
 

@@ -218,9 +218,20 @@ typedef struct cg_cl_desc {
   float* out;
   long long out_group_stride;
   int max_ctas;
+  int n_seg, seg_stride;       /* CG_GROUP_SAMPLE: a group also covers slots slot_lo+g + s*seg_stride, s < n_seg
+                                  (per-sample sum over passes, accum_passes=True); 0/1 = single slot       */
 } cg_cl_desc;
 
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream);
+
+/* Joint clipping (accum_passes=True: the per-sample gradients of all passes are summed before clipping).
+ * Cross terms of the Linear closed form ||sum_p b_p a_p^T||^2 = sum_{p,p'} (a_p.a_p')(b_p.b_p'):
+ *   out[n] (+)= < T[:, row_a+n, :], T[:, row_b+n, :] >   over a chunk-major matrix T[n_chunks][rows_total][32] */
+int cg_rowpair_dot(const float* T, long long rows_total, int n_chunks, int row_a, int row_b, int B, float* out,
+                   int accumulate, cg_stream_t stream);
+/* out[n] = || sum_{s<n_seg} rows_in[slot_lo + n + s*seg_stride][0:R] ||^2   (joint per-sample bias norms) */
+int cg_joint_rows_sumsq(const float* rows_in, int R, int slot_lo, int seg_stride, int n_seg, int B, float* out,
+                        cg_stream_t stream);
 
 /* out[n][m][p] = Xt[m/32][slot0+n][m%32] * Yt[p/32][slot0+n][p%32]  (materialised Linear per-sample
  * gradients; x_rows / y_rows = rows of each chunk) */
@@ -238,6 +249,9 @@ int cg_row_sumsq(const float* src, long long rows, long long cols, long long ld,
 
 /* out[i] = a[i] * b[i]  (closed-form Linear norm ||b a^T||_F^2 = ||a||^2 ||b||^2). */
 int cg_vec_mul(const float* a, const float* b, float* out, long long n, cg_stream_t stream);
+
+/* out[i] += w * a[i] * b[i]  (pairwise terms of the joint Linear norm). */
+int cg_vec_fma(const float* a, const float* b, float w, float* out, long long n, cg_stream_t stream);
 
 /* Clip factors (replaces norm_clipper.calc_clipping_factors, reference train.py:324-328):
  *   norm2 [n_params][n_slots] squared per-parameter norms.

@@ -185,6 +185,45 @@ def test_gc_step_matches_oracle(name, B, C):
         assert rel(got["grads"][k], ref["grads"][k]) < REL_TOL or err / B <= floor / B
 
 
+@pytest.mark.parametrize("name,B,C", [("mnist", 40, "median"), ("mnist_dcrn", 7, "median"), ("d64", 4, "median-pl"),
+                                      ("mnist", 64, [3.0, 0.2, 0.5, 0.2, 1.0, 0.5])])
+def test_gc_joint_clipping_accum_passes(name, B, C):
+    """U2 (-gcs False): accum_passes=True sums fake_i + real_i per sample and clips the sum once."""
+    D, shape, ncls, lo = make(name)
+    real, fake, y = batch(shape, ncls, lo, B, seed=B + 100)
+
+    def oracle(Cv):
+        Dm = copy.deepcopy(D)
+        eng = O.OracleGCEngine(Dm, batch_size=B, noise_multiplier=0.0, max_grad_norm=Cv, accum_passes=True,
+                               num_private_passes=None)
+        d_loss(Dm, real, fake, y).backward()
+        captured = [dict(eng.captured[k]) for k in sorted(eng.captured)]
+        norms = eng.sample_norms()
+        pp = O.calc_sample_norms(eng.grad_samples(), flat=False)
+        eng.clip(); eng.accumulate_batch(); eng.step_grads(None)
+        return norms, pp, [p.grad.clone() for p in eng.params()], captured
+
+    if isinstance(C, str):
+        norms, pp, _, _ = oracle(1e9)
+        C = float(norms[0].median()) if C == "median" else [float(n.median()) for n in pp]
+    norms, pp, grads, captured = oracle(C)
+    assert norms[0].shape[0] == 1                                   # one joint "pass"
+    Dg = copy.deepcopy(D).to(DEV)
+    opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+    eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=1000, noise_multiplier=0.0, max_grad_norm=C,
+                           accum_passes=True, num_private_passes=None, auto_clip_and_accum_on_step=False)
+    eng.attach(opt)
+    eng.ingest_captures([{n: (a.to(DEV), g.to(DEV)) for n, (a, g) in layers.items()} for layers in captured])
+    got_pp = eng.per_sample_norms()
+    assert tuple(got_pp.shape) == (len(pp), 1, B)
+    for k, b in enumerate(pp):
+        np.testing.assert_allclose(got_pp[k].cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+    eng.clip(); eng.accumulate_batch()
+    opt.step()
+    for p, g in zip(Dg.parameters(), grads):
+        assert rel(p.grad, g) < REL_TOL
+
+
 def test_lazy_grad_sample_view_and_materialize():
     D, shape, ncls, lo = make("mnist_dcrn")
     B = 5
