@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--workload", choices=["celeba_d64_gc", "mnist_gc"], default="celeba_d64_gc")
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch size (weak scaling)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads / cpu baseline")
+    ap.add_argument("--no-graph", action="store_true", help="run the e2e step eagerly instead of as one CUDA graph")
     return ap.parse_args()
 
 
@@ -121,7 +122,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -275,7 +276,8 @@ def main():
         D = D.to(memory_format=torch.channels_last)          # cuDNN's native tensor-core layout for the critic itself
     real_pin, fake_pin = real_h.pin_memory(), fake_h.pin_memory()
     y_dev = None if y_h is None else y_h.to(dev)
-    opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9) if wl == "celeba_d64_gc" else (0.9, 0.999))
+    opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9) if wl == "celeba_d64_gc" else (0.9, 0.999),
+                             capturable=True)
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=cfg["sample_size"], noise_multiplier=cfg["sigma"],
                            max_grad_norm=cfg["C"], accum_passes=False, num_private_passes=1,
                            auto_clip_and_accum_on_step=False, data_parallel=dist_on)
@@ -293,10 +295,29 @@ def main():
         eng.accumulate_batch()
         eng.step()
 
+    # single GPU: the DP machinery is captured once into a CUDA graph and replayed (launch-bound at MNIST sizes);
+    # with several ranks it stays eager because engine.step() issues the NCCL allreduce from Python
+    use_graph = not args.no_graph and not dist_on
     launches0 = L.launch_count
-    with ClockSampler(local) as clk:
-        ms_dp = timed(dp_only, args.steps, args.warmup, dist_on)
-    launches = (L.launch_count - launches0) // (args.steps + args.warmup)      # ABI launch calls per step
+    dp_only()
+    launches = L.launch_count - launches0                                       # ABI launch calls per step
+    timed_fn = dp_only
+    if use_graph:
+        eng.enable_graph_safe_rng()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                dp_only()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        dp_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(dp_graph):
+            dp_only()
+        timed_fn = dp_graph.replay
+    clk = ClockSampler(local)
+    clk.__enter__()                      # sampled across both timed regions (t_dp below, e2e further down)
+    ms_dp = timed(timed_fn, args.steps, args.warmup, dist_on)
     t_dp = ms_dp / args.steps
     value = B * world / (t_dp * 1e-3)
 
@@ -334,19 +355,30 @@ def main():
             staged["ev"].record(copy_stream)
 
     upload()
+    # one CUDA graph for the whole step (critic fwd/bwd, capture, norms, clip, noise, Adam) on a single GPU;
+    # with several ranks the step stays eager (the NCCL allreduce is issued from Python)
+    runner = None
+    if use_graph:
+        from csl_gan_b200.dstep import GraphedDiscriminatorStep
+        runner = GraphedDiscriminatorStep(stepper, (staged["r"], y_dev, staged["f"], y_dev), warmup=3)
 
     def e2e_step():
         torch.cuda.current_stream().wait_event(staged["ev"])
         r, f = staged["r"], staged["f"]
         r.record_stream(torch.cuda.current_stream())
         f.record_stream(torch.cuda.current_stream())
-        upload()                                                    # next step's inputs, overlapped
-        res = stepper(r, y_dev, f, y_dev, use_dp=True)
+        if runner is not None:
+            res = runner(r, y_dev, f, y_dev)                        # copies into the graph's static inputs, then replays
+            upload()                                                # next step's inputs, overlapped
+        else:
+            upload()
+            res = stepper(r, y_dev, f, y_dev, use_dp=True)
         return (res.d_real_loss + res.d_fake_loss).item()          # D2H read of the step's result
 
     ms_e2e = timed(e2e_step, args.steps, args.warmup, dist_on)
     e2e_value = B * world / (ms_e2e / args.steps * 1e-3)
     h2d = real_pin.numel() * 4 + fake_pin.numel() * 4
+    clk.__exit__(None, None, None)
     clocks = clk.summary()
 
     if rank == 0:
@@ -373,17 +405,20 @@ def main():
         line = {
             "metric": "per-sample clipped grads/sec (DP D-step)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dp,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands, f32 accumulate",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
             "data": "synthetic",
             "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "n_passes": 2,
                        "contractions_per_step": 2 * B * world, "clipping": "per-layer" if isinstance(cfg["C"], list) else "flat",
                        "sigma": cfg["sigma"], "parallelism": f"dp{world}",
+                       "arithmetic": "TF32 tensor-core operands (round-to-nearest staged), fp32 accumulation and fp32 everywhere else",
                        "l2": "staged operands per step exceed the 126 MB L2 (no flush needed)" if wl == "celeba_d64_gc"
                              else "working set fits in L2; MNIST is launch-latency bound (SURVEY.md §8d)"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "mode": "cuda-graph replay of DiscriminatorStep" if use_graph else "eager DiscriminatorStep"},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
+            "launch_mode": "cuda-graph replay" if use_graph else "eager",
             "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][0])},
             "roofline": roof,
             "clocks": clocks,

@@ -117,6 +117,10 @@ _PROTOS = {
                                     C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_void_p]),
     "cg_noise_finalize_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p,
                                         C.c_double, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_void_p]),
+    "cg_noise_finalize_graph": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p,
+                                          C.c_double, C.c_ulonglong, C.c_void_p, C.c_ulonglong,
+                                          C.POINTER(C.c_ulonglong), C.c_void_p]),
+    "cg_philox_advance": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     "cg_row_l2_norm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_row_l2_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_vec_max": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),

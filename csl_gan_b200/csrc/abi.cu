@@ -738,7 +738,8 @@ int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int sl
 
 static int noise_impl(const float* in, float* grad, long long n, double in_div, double std, const float* std_dev,
                       double noise_div, unsigned long long seed, unsigned long long offset,
-                      unsigned long long* offset_inc, cg_stream_t stream) {
+                      unsigned long long* offset_inc, cg_stream_t stream,
+                      const unsigned long long* offset_dev = nullptr) {
   if (offset_inc) *offset_inc = 0;
   if (n <= 0) return 0;
   DevInfo d;
@@ -760,7 +761,7 @@ static int noise_impl(const float* in, float* grad, long long n, double in_div, 
   if (grid > cap) grid = cap;
   if (offset_inc) *offset_inc = ((static_cast<unsigned long long>(n) - 1) / (block * grid * 4) + 1) * 4;
   cg::noise_finalize_kernel<<<static_cast<unsigned int>(grid), block, 0, S(stream)>>>(
-      in, grad, n, recip(in_div), static_cast<float>(std), recip(noise_div), seed, offset, std_dev);
+      in, grad, n, recip(in_div), static_cast<float>(std), recip(noise_div), seed, offset, std_dev, offset_dev);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -769,6 +770,22 @@ int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, 
                       unsigned long long seed, unsigned long long offset, unsigned long long* offset_inc,
                       cg_stream_t stream) {
   return noise_impl(in, grad, n, in_div, std, nullptr, noise_div, seed, offset, offset_inc, stream);
+}
+
+int cg_noise_finalize_graph(const float* in, float* grad, long long n, double in_div, double std_mult,
+                            const float* std_dev, double noise_div, unsigned long long seed,
+                            const unsigned long long* offset_dev, unsigned long long intra_offset,
+                            unsigned long long* offset_inc, cg_stream_t stream) {
+  if (!offset_dev) return fail("offset_dev must not be null");
+  return noise_impl(in, grad, n, in_div, std_mult, std_dev, noise_div, seed, intra_offset, offset_inc, stream,
+                    offset_dev);
+}
+
+int cg_philox_advance(unsigned long long* offset_dev, unsigned long long inc, cg_stream_t stream) {
+  if (!offset_dev) return fail("offset_dev must not be null");
+  cg::philox_advance_kernel<<<1, 32, 0, S(stream)>>>(offset_dev, inc);
+  CG_LAUNCH_CHECK();
+  return 0;
 }
 
 int cg_noise_finalize_dev(const float* in, float* grad, long long n, double in_div, double std_mult,

@@ -416,8 +416,12 @@ __global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4)
 noise_finalize_kernel(const float* in, float* grad, long long numel, float in_mul, float stdv, float noise_mul,
-                      unsigned long long seed, unsigned long long offset, const float* __restrict__ std_dev) {
+                      unsigned long long seed, unsigned long long offset, const float* __restrict__ std_dev,
+                      const unsigned long long* __restrict__ offset_dev) {
   if (std_dev) stdv = __fmul_rn(stdv, std_dev[0]);
+  // CUDA-graph mode: the generator offset lives in device memory (like torch's captured PhiloxCudaState);
+  // `offset` is then the intra-step displacement
+  if (offset_dev) offset += offset_dev[0];
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   curandStatePhilox4_32_10_t state;
   curand_init(seed, idx, offset, &state);
@@ -444,6 +448,10 @@ noise_finalize_kernel(const float* in, float* grad, long long numel, float in_mu
       }
     }
   }
+}
+
+__global__ void philox_advance_kernel(unsigned long long* offset_dev, unsigned long long inc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) offset_dev[0] += inc;
 }
 
 // no-noise variant (sigma == 0 or C == 0): grad = in / in_div

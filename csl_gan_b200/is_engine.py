@@ -86,9 +86,21 @@ class ISPrivacyEngine:
     def _set_seed(self, seed: int):
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._philox_offset = 0
+        if getattr(self, "_offset_dev", None) is not None:
+            self._offset_dev.zero_()
+
+    def enable_graph_safe_rng(self):
+        """Philox offset in device memory: a CUDA-graph-captured step draws fresh noise at every replay."""
+        if getattr(self, "_offset_dev", None) is None:
+            self._offset_dev = torch.tensor([self._philox_offset], dtype=torch.int64, device=self.device)
+
+    @property
+    def philox_offset(self) -> int:
+        od = getattr(self, "_offset_dev", None)
+        return int(od.item()) if od is not None else self._philox_offset
 
     def state_dict(self) -> Dict:
-        return {"steps": self.steps, "seed": self._seed, "philox_offset": self._philox_offset,
+        return {"steps": self.steps, "seed": self._seed, "philox_offset": self.philox_offset,
                 "scaling_vec": self.scaling_vec}
 
     def load_state_dict(self, sd: Dict):
@@ -182,6 +194,8 @@ class ISPrivacyEngine:
         st = L.stream_ptr(self.device)
         inc = C.c_ulonglong(0)
         ndiv = float(self.batch_size) if self.noise_div_batch else 0.0
+        od = getattr(self, "_offset_dev", None)
+        intra = 0
         for k, p in enumerate(self._params):
             mult = self.noise_multiplier
             if self.per_param:
@@ -191,9 +205,16 @@ class ISPrivacyEngine:
                 if self.scaling_vec is not None:
                     mult *= self.scaling_vec[k]
             g = p.grad
-            L.call("cg_noise_finalize_dev", L.ptr(g), L.ptr(g), g.numel(), 0.0, mult, L.ptr(sdev), ndiv,
-                   self._seed, self._philox_offset, C.byref(inc), st)
-            self._philox_offset += inc.value
+            if od is not None:
+                L.call("cg_noise_finalize_graph", L.ptr(g), L.ptr(g), g.numel(), 0.0, mult, L.ptr(sdev), ndiv,
+                       self._seed, L.ptr(od), intra, C.byref(inc), st)
+                intra += inc.value
+            else:
+                L.call("cg_noise_finalize_dev", L.ptr(g), L.ptr(g), g.numel(), 0.0, mult, L.ptr(sdev), ndiv,
+                       self._seed, self._philox_offset, C.byref(inc), st)
+                self._philox_offset += inc.value
+        if od is not None and intra:
+            L.call("cg_philox_advance", L.ptr(od), intra, st)
 
     # ------------------------------------------------------------------ accountant
     def get_privacy_spent(self, target_delta: Optional[float] = None):

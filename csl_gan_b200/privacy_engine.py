@@ -278,15 +278,30 @@ class PrivacyEngine:
         device; reference train.py:136).  State = (seed, offset) exactly like a CUDA generator."""
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._philox_offset = 0
+        if getattr(self, "_offset_dev", None) is not None:
+            self._offset_dev.zero_()
+
+    def enable_graph_safe_rng(self):
+        """Keep the Philox offset in device memory so a CUDA-graph-captured step draws fresh noise on every
+        replay (the host counter would be frozen into the captured kernel arguments)."""
+        if getattr(self, "_offset_dev", None) is None:
+            self._offset_dev = torch.tensor([self._philox_offset], dtype=torch.int64, device=self.device)
+
+    @property
+    def philox_offset(self) -> int:
+        od = getattr(self, "_offset_dev", None)
+        return int(od.item()) if od is not None else self._philox_offset
 
     # checkpointing of the engine state the reference forgets (SURVEY.md §5: accountant restarts on resume)
     def state_dict(self) -> Dict:
-        return {"steps": self.steps, "seed": self._seed, "philox_offset": self._philox_offset,
+        return {"steps": self.steps, "seed": self._seed, "philox_offset": self.philox_offset,
                 "max_grad_norm": self.max_grad_norm}
 
     def load_state_dict(self, sd: Dict):
         self.steps = sd["steps"]
         self._seed, self._philox_offset = sd["seed"], sd["philox_offset"]
+        if getattr(self, "_offset_dev", None) is not None:
+            self._offset_dev.fill_(self._philox_offset)
         self.set_max_grad_norm(sd["max_grad_norm"])
 
     # ------------------------------------------------------------------ hooks
@@ -642,20 +657,34 @@ class PrivacyEngine:
         st = L.stream_ptr(self.device)
         inc = C.c_ulonglong(0)
         host = self._thresholds_host
+        od = getattr(self, "_offset_dev", None)
+        intra = 0
         for k, p in enumerate(self._params):
             s = p.summed_grad
             g = torch.empty_like(p)
-            if host is not None:
+            if od is not None:
+                if host is not None:
+                    mult, cdev = self.noise_multiplier * (host[k] if self._per_layer else host[0]), None
+                else:
+                    mult = self.noise_multiplier
+                    cdev = self._thresholds_dev[k:k + 1] if self._per_layer else self._thresholds_dev[:1]
+                L.call("cg_noise_finalize_graph", L.ptr(s), L.ptr(g), s.numel(), div, mult, L.ptr(cdev), div,
+                       self._seed, L.ptr(od), intra, C.byref(inc), st)
+                intra += inc.value
+            elif host is not None:
                 std = self.noise_multiplier * (host[k] if self._per_layer else host[0])
                 L.call("cg_noise_finalize", L.ptr(s), L.ptr(g), s.numel(), div, std, div,
                        self._seed, self._philox_offset, C.byref(inc), st)
+                self._philox_offset += inc.value
             else:
                 cdev = self._thresholds_dev[k:k + 1] if self._per_layer else self._thresholds_dev[:1]
                 L.call("cg_noise_finalize_dev", L.ptr(s), L.ptr(g), s.numel(), div, self.noise_multiplier,
                        L.ptr(cdev), div, self._seed, self._philox_offset, C.byref(inc), st)
-            self._philox_offset += inc.value
+                self._philox_offset += inc.value
             p.grad = g
             p.summed_grad = None
+        if od is not None and intra:
+            L.call("cg_philox_advance", L.ptr(od), intra, st)
         self._accum_bs = 0
 
     def _allreduce_summed(self, bs: float) -> float:

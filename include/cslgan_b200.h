@@ -303,6 +303,15 @@ int cg_noise_finalize_dev(const float* in, float* grad, long long n, double in_d
                           const float* std_dev, double noise_div, unsigned long long seed,
                           unsigned long long offset, unsigned long long* offset_inc, cg_stream_t stream);
 
+/* CUDA-graph variant: the generator offset is read from DEVICE memory (offset_dev[0] + intra_offset), so a
+ * captured step draws fresh noise at every replay; std = std_mult * (std_dev ? std_dev[0] : 1).
+ * cg_philox_advance bumps the device offset once per step (captured as the step's last node). */
+int cg_noise_finalize_graph(const float* in, float* grad, long long n, double in_div, double std_mult,
+                            const float* std_dev, double noise_div, unsigned long long seed,
+                            const unsigned long long* offset_dev, unsigned long long intra_offset,
+                            unsigned long long* offset_inc, cg_stream_t stream);
+int cg_philox_advance(unsigned long long* offset_dev, unsigned long long inc, cg_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Per-sample row norms (reference gradient_penalty.py:52-53, 60-61; immediate sensitivity,
  * train.py:457/469) and per-sample L2 clipping (reference backprop_clip.py:18-22)

@@ -87,3 +87,48 @@ def test_readme_invocations():
     _run(["MNIST", "--dp_mode", "gc", "-gcm", "constant-pl", "-cpl", "1.0"], B=16)
     # scaled flat immediate sensitivity with the moving-average update
     _run(["MNIST", "--dp_mode", "is", "-issm", "moving-avg-pl", "-issv", "1", "1", "1", "1"], B=16)
+
+
+def test_cuda_graph_step_matches_eager_and_draws_fresh_noise():
+    """GraphedDiscriminatorStep: same weights as the eager step after several noisy steps (same seed), which
+    also proves every replay consumes a fresh part of the Philox stream."""
+    import copy
+    from csl_gan_b200.dstep import GraphedDiscriminatorStep
+    B = 32
+    results = {}
+    for mode in ("eager", "graph"):
+        opt = OPT.parse(["MNIST", "-dpm", "gc", "--conditional", "--sigma", "2", "-bs", str(B), "-tss", "1000", "--manual_seed", "5"])
+        D = DD.build_discriminator("MNIST", "Vanilla", n_classes=10, conditional_arch="ACGAN", aux_loss_type="cross_entropy",
+                                   weights_seed=42, device=DEV)
+        d_opt = torch.optim.Adam(D.parameters(), lr=1e-3, capturable=True)
+        eng = setup_privacy_engine(opt, D, d_opt)
+        stepper = DiscriminatorStep(opt, D, d_opt, eng)
+        g = torch.Generator().manual_seed(1)
+        batches = [(torch.rand(B, 1, 28, 28, generator=g).to(DEV), torch.randint(0, 10, (B,), generator=g).to(DEV),
+                    torch.rand(B, 1, 28, 28, generator=g).to(DEV)) for _ in range(7)]
+        if mode == "graph":
+            eng.enable_graph_safe_rng()
+        # the first 3 steps run eagerly in both modes (PyTorch wants cuBLAS/cuDNN warmed up on a side stream
+        # before a capture); the graph then replays steps 4..7
+        if mode == "graph":
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for x, y, f in batches[:3]:
+                    out = stepper(x, y, f, y, use_dp=True)
+            torch.cuda.current_stream().wait_stream(side)
+            x, y, f = batches[3]
+            runner = GraphedDiscriminatorStep(stepper, (x, y, f, y), warmup=0)
+            for x, y, f in batches[3:]:
+                out = runner(x, y, f, y)
+        else:
+            for x, y, f in batches:
+                out = stepper(x, y, f, y, use_dp=True)
+        torch.cuda.synchronize()
+        results[mode] = ([p.detach().clone() for p in D.parameters()], eng.philox_offset, eng.steps,
+                         out.to_host()["D Adv Loss"])
+    for a, b in zip(results["eager"][0], results["graph"][0]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert results["eager"][1] == results["graph"][1] > 0          # same amount of Philox stream consumed
+    assert results["eager"][2] == results["graph"][2] == 7
+    assert abs(results["eager"][3] - results["graph"][3]) < 1e-4
