@@ -192,6 +192,45 @@ def measure_tf32_peak():
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
+def bandwidth_kernels(hbm_peak_gbs):
+    """Achieved HBM GB/s of the bandwidth-bound kernels (noise add, per-sample row norm, l2_clip) on buffers
+    larger than the 126 MB L2, against the measured copy bandwidth.  Algorithmic bytes:
+    noise 8 B per parameter element, row norm 4 B per input element, l2_clip 8 B per element."""
+    import ctypes as C
+    from csl_gan_b200 import _lib as L
+    from csl_gan_b200 import functional as FN
+    out = {}
+
+    def time_it(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    n = 96 * 1024 * 1024                                   # 384 MB per fp32 buffer
+    a = torch.randn(n, device="cuda")
+    b = torch.empty_like(a)
+    inc = C.c_ulonglong(0)
+    t = time_it(lambda: L.call("cg_noise_finalize", a.data_ptr(), b.data_ptr(), n, 512.0, 0.5, 512.0, 1, 0,
+                               C.byref(inc), L.stream_ptr()))
+    out["noise_finalize"] = {"elements": n, "GB/s": 8 * n / t / 1e9}
+    rows = 8192
+    x = a[: rows * 12288].view(rows, 12288)                # 8192 rows of a [B, 3*64*64] input gradient: 403 MB
+    t = time_it(lambda: FN.row_l2_norm(x))
+    out["row_l2_norm"] = {"shape": [rows, 12288], "GB/s": 4 * x.numel() / t / 1e9}
+    t = time_it(lambda: FN.l2_clip(x, 50.0))
+    out["l2_clip"] = {"shape": [rows, 12288], "GB/s": 8 * x.numel() / t / 1e9}
+    for v in out.values():
+        v["frac_of_measured_hbm_peak"] = v["GB/s"] / hbm_peak_gbs if hbm_peak_gbs else None
+    return out
+
+
 def cpu_step_rate(workload: str, B: int, steps: int, warmup: int):
     """Full DP D-step of the CPU oracle (fwd fake+real, backward with grad-sample hooks, norms, clip,
     weighted sum, accumulate, noise) on all host cores; returns (samples/s, ms/step, cores)."""
@@ -424,6 +463,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_extras and world == 1:
+            line["bandwidth_kernels"] = bandwidth_kernels(peaks.get("hbm_gbs"))
             Bc = 64 if wl == "celeba_d64_gc" else 600
             rate, ms, cores = cpu_step_rate(wl, Bc, 3, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
