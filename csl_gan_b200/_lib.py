@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcslgan_b200.so")
 CG_MAX_KH = 16
-EPI_SUMSQ, EPI_ACCUM, EPI_STORE = 0, 1, 2
+EPI_SUMSQ, EPI_ACCUM, EPI_STORE, EPI_STORE_NATURAL = 0, 1, 2, 3
 GROUP_SAMPLE, GROUP_SPLITK = 0, 1
 
 

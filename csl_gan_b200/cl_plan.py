@@ -101,6 +101,10 @@ class ClLayerPlan:
         self.T = torch.zeros((M, self.ldT), device=dev)
         # ghost norms when Q | 128 (needs the un-merged plan, which is what small-Q layers have)
         self.ghost = ghost_ok
+        # thin layers: materialise the (small) per-sample gradients once instead of contracting twice
+        self.thin = (self.kind != "linear" and not self.ghost and self.Q >= 256 and M * self.ldT <= 16384)
+        self.Gs = torch.zeros((S, M * self.ldT), device=dev) if self.thin else None
+        self._gs_joint = 1
         if self.kind == "convT" and self.b_idx is not None:
             self._bias_scratch = torch.empty((_round_up(self.bias_len, 32) // 32, Bpad * H * W, 32), device=dev)
             self._HW = (H, W)
@@ -189,6 +193,15 @@ class ClLayerPlan:
         d = self._desc(self.Xt)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
         d.n_seg, d.seg_stride = n_joint, self.Bpad
+        if self.thin:
+            # G[slot][m][tap][c'] once (joint mode: the per-sample sum over passes lands in pass 0's slots);
+            # the norms are then a row reduction over |theta_layer| floats per sample
+            R = self.Gs.shape[1]
+            d.epi, d.out, d.out_group_stride = L.EPI_STORE_NATURAL, L.ptr(self.Gs[slot0:]), R
+            L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
+            L.call("cg_row_sumsq", L.ptr(self.Gs[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
+            self._gs_joint = n_joint
+            return
         d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
         L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
 
@@ -209,11 +222,16 @@ class ClLayerPlan:
     def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0):
         """Xc = tf32(Xt * factor[slot - factor_shift]): every chunk of Xt is a row of slot-sized (Q*32) segments.
         factor_shift != 0 reuses pass 0's (joint) factors for a later pass."""
+        if self.thin:
+            return                      # the clipped sum comes from the materialised per-sample gradients
         L.call("cg_scale_slots", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * 32, self.Q * 32,
                slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, L.stream_ptr(factor_row.device))
 
-    def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
+    def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool,
+                     factor_row: Optional[torch.Tensor] = None):
         st = L.stream_ptr(out_w.device)
+        if self.thin:
+            return self._thin_weighted_sum(out_w, slot_lo, slot_hi, accumulate, factor_row, st)
         d = self._desc(self.Xc)
         # tiles per K range (mirror of cg_cl_contract) -> split K so the grid covers the machine ~2x
         n_cb, n_taps = self.n_cb, self.plan.n_taps
@@ -255,6 +273,26 @@ class ClLayerPlan:
                    1 if (accumulate and dst is out_w) else 0, st)
             if dst is not out_w:
                 out_w.add_(dst) if accumulate else out_w.copy_(dst)
+
+    def _thin_weighted_sum(self, out_w, slot_lo, slot_hi, accumulate, factor_row, st):
+        """sum_slot factor[slot] * G[slot] over the materialised per-sample gradients (natural layout)."""
+        if factor_row is None:
+            raise L.CslGanCudaError(f"{self.name}: the thin-layer path needs the clip factors")
+        if self._gs_joint > 1:
+            slot_hi = min(slot_hi, slot_lo + self.Bpad)       # joint sums live in pass 0's slots only
+        R = self.Gs.shape[1]
+        natural = None
+        if (out_w.dim() == 4 and not out_w.is_contiguous()
+                and out_w.is_contiguous(memory_format=torch.channels_last)):
+            natural = out_w.permute(0, 2, 3, 1)               # [m][kh][kw][c] == T[m][tap][c'] (merged or not)
+        target = natural if natural is not None else self.T
+        L.call("cg_weighted_colsum", L.ptr(self.Gs), L.ptr(factor_row), slot_lo, slot_hi, R, L.ptr(target),
+               1 if (accumulate and natural is not None) else 0, st)
+        if natural is None:
+            if not out_w.is_contiguous():
+                raise L.CslGanCudaError(f"{self.name}: unsupported weight memory layout {out_w.stride()}")
+            L.call("cg_permute_accum", L.ptr(self.T), L.ptr(out_w), self.M, self.Cn, self.KH, self.KW,
+                   1 if accumulate else 0, st)
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
                           accumulate: bool, factor_shift: int = 0):

@@ -257,8 +257,10 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) atomicAdd(p.out + c.g, ss);
-      } else if (p.epi == CG_EPI_ACCUM) {
-        // T[m][tap*C + c]: one 32-channel chunk = 128 contiguous bytes per row -> coalesced reductions
+      } else if (p.epi == CG_EPI_ACCUM || p.epi == CG_EPI_STORE_NATURAL) {
+        // T[m][tap*C + c]: one 32-channel chunk = 128 contiguous bytes per row -> coalesced reductions / stores
+        const bool store = p.epi == CG_EPI_STORE_NATURAL;
+        float* const obase_nat = p.out + (store ? static_cast<long long>(c.g) * p.out_group_stride : 0);
         for (int j = 0; j < nbv; ++j) {
           float v[16];
           tmem_ld16(taddr + j * 32, v);
@@ -272,9 +274,14 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
           const int tap = c.tap0 + tl, cb = c.cb0 + (j - tl * c.ncb);
           const int ch = cb * 32 + lane;
           if (ch < p.C) {
-            float* o = p.out + static_cast<long long>(tap) * p.C + ch;
-            for (int r = 0; r < 32; ++r)
-              if (row0 + r < p.M) atomicAdd(o + static_cast<long long>(row0 + r) * p.ldT, tbuf[r * 33 + lane]);
+            float* o = obase_nat + static_cast<long long>(tap) * p.C + ch;
+            if (store) {
+              for (int r = 0; r < 32; ++r)
+                if (row0 + r < p.M) o[static_cast<long long>(row0 + r) * p.ldT] = tbuf[r * 33 + lane];
+            } else {
+              for (int r = 0; r < 32; ++r)
+                if (row0 + r < p.M) atomicAdd(o + static_cast<long long>(row0 + r) * p.ldT, tbuf[r * 33 + lane]);
+            }
           }
           __syncwarp();
         }

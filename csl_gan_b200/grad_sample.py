@@ -256,10 +256,12 @@ class LayerPlan:
         L.call("cg_scale_slots", L.ptr(self.X), L.ptr(self.Xc), self.M, self.X.stride(0), self.x_slot_stride,
                slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, st)
 
-    def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool):
-        """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots."""
+    def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool,
+                     factor_row: Optional[torch.Tensor] = None):
+        """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots (factor_row is only
+        used by the thin-layer path of the channels-last plan, which sums materialised per-sample gradients)."""
         if self.impl is not None:
-            return self.impl.weighted_sum(out_w, slot_lo, slot_hi, sm_count, accumulate)
+            return self.impl.weighted_sum(out_w, slot_lo, slot_hi, sm_count, accumulate, factor_row)
         st = L.stream_ptr(out_w.device)
         d = self._desc(self.Xc)
         # mirror of the tile choice in cg_contract (csrc/abi.cu)

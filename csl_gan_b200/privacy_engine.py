@@ -588,10 +588,11 @@ class PrivacyEngine:
                 plan.scale_backprops(frow_w, lo, hi, shift)
             if joint or len(ranges) == 1:
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
-                plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False)
+                plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False,
+                                  factor_row=frow_w)
             else:
                 for i, (lo, hi, _) in enumerate(ranges):
-                    plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0)
+                    plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0, factor_row=frow_w)
             if plan.b_idx is not None:
                 frow_b = self._factors[plan.b_idx if self._per_layer else 0]
                 for i, (lo, hi, shift) in enumerate(ranges):

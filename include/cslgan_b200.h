@@ -108,7 +108,12 @@ int cg_stage_unfold(const float* src, int B, const cg_unfold_geom* g, const cg_u
  *   CG_EPI_STORE  out[group][m][c][kh][kw] = tile (materialise grad_sample for the rare
  *                 consumers: train.py:233, 447 and tests)
  * ------------------------------------------------------------------------------------------- */
-enum { CG_EPI_SUMSQ = 0, CG_EPI_ACCUM = 1, CG_EPI_STORE = 2 };
+enum { CG_EPI_SUMSQ = 0, CG_EPI_ACCUM = 1, CG_EPI_STORE = 2,
+       /* cg_cl_contract only: out[group][m][tap][c'] = tile in the gradient-natural layout, coalesced.  For THIN
+          layers (few parameters, huge operands: the 3-channel first conv) materialising the per-sample gradients
+          (|theta_layer| floats per sample) is far cheaper than contracting twice: norms and the clipped sum are
+          then a row_sumsq and a weighted column sum over that small tensor. */
+       CG_EPI_STORE_NATURAL = 3 };
 enum { CG_GROUP_SAMPLE = 0, CG_GROUP_SPLITK = 1 };
 
 typedef struct cg_contract_desc {

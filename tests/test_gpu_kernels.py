@@ -140,7 +140,7 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d,
     f = torch.rand(Bpad, device=DEV) + 0.25
     plan.scale_backprops(f, 0, B)
     out = torch.empty_like(conv.weight)
-    plan.weighted_sum(out, 0, B, 148, accumulate=False)
+    plan.weighted_sum(out, 0, B, 148, accumulate=False, factor_row=f)     # factor_row: thin-layer path only
     torch.cuda.synchronize()
     ref = torch.einsum("n,n...->...", f[:B].cpu(), gw_ref)
     assert ((out.cpu() - ref).norm() / ref.norm()).item() < 1e-3
