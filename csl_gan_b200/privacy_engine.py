@@ -501,6 +501,17 @@ class PrivacyEngine:
         else:
             L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 0, L.ptr(self._thresholds_dev), clip_lo, clip_hi,
                    L.ptr(self._factors), L.ptr(self._flat_norms), st)
+        # slots past the live batch of a pass (batch smaller than the padded slot count) may hold the staged
+        # rows of an earlier, larger step; clip() contracts whole slot ranges, so their factor must be 0
+        fv = self._factors.view(self._factors.shape[0], self.max_passes, self.Bpad)
+        live_b = [self._pass_B[ps] for ps in range(self._n_passes())]
+        if len(set(live_b)) == 1:
+            if live_b[0] < self.Bpad:
+                fv[:, :len(live_b), live_b[0]:].zero_()
+        else:
+            for ps, b in enumerate(live_b):
+                if b < self.Bpad:
+                    fv[:, ps, b:].zero_()
         self._factors_valid = True
 
     def _slot_view(self, t: torch.Tensor) -> torch.Tensor:
@@ -585,7 +596,9 @@ class PrivacyEngine:
                 ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], 0) for ps in live]
             frow_w = self._factors[plan.w_idx if self._per_layer else 0]
             for lo, hi, shift in ranges:
-                plan.scale_backprops(frow_w, lo, hi, shift)
+                # scale up to the next 32-slot boundary (Bpad is a multiple of 32, dead slots have factor 0):
+                # the contraction reads whole 32-row K blocks, which may reach past `hi` when Q < 32
+                plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
             if joint or len(ranges) == 1:
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
                 plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False,

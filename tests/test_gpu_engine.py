@@ -224,6 +224,29 @@ def test_gc_joint_clipping_accum_passes(name, B, C):
         assert rel(p.grad, g) < REL_TOL
 
 
+@pytest.mark.parametrize("name,sizes", [("mnist_dcrn", (40, 13, 40, 1)), ("d48", (12, 5, 9))])
+def test_smaller_last_batch_and_engine_reuse_across_steps(name, sizes):
+    """A batch smaller than the configured batch_size (last batch of an epoch) and several consecutive steps on
+    one engine: buffers are reused, stale slots of the previous (larger) step must not leak in."""
+    D, shape, ncls, lo = make(name)
+    Dg = copy.deepcopy(D).to(DEV)
+    opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+    eng = cg.PrivacyEngine(Dg, batch_size=sizes[0], sample_size=1000, noise_multiplier=0.0, max_grad_norm=0.4,
+                           num_private_passes=1, auto_clip_and_accum_on_step=False)
+    eng.attach(opt)
+    for B in sizes:
+        real, fake, y = batch(shape, ncls, lo, B, seed=50 + B)
+        ref = run_oracle(copy.deepcopy(D), real, fake, y, B, 0.4)
+        eng.enable_hooks()
+        eng.ingest_captures([{n: (a.to(DEV), g.to(DEV)) for n, (a, g) in layers.items()} for layers in ref["captured"]])
+        eng.disable_hooks()
+        eng.clip(); eng.accum_grads_across_passes(); eng.accumulate_batch()
+        opt.step()
+        for p, g in zip(Dg.parameters(), ref["grads"]):
+            assert rel(p.grad, g) < REL_TOL, B
+    assert eng.steps == len(sizes)
+
+
 def test_lazy_grad_sample_view_and_materialize():
     D, shape, ncls, lo = make("mnist_dcrn")
     B = 5
