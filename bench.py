@@ -437,9 +437,9 @@ def main():
                 "contract_launches_per_step": n_contract,
                 "whole_dp_frac": flops_step / (t_dp * 1e-3) / 1e12 / tf32_peak,
                 # dram__bytes_read+write summed over the contraction launches of one step, from the ncu --set full
-                # capture in profiles/r1_ncu_full_contraction_kernels.txt (B=512/GPU CelebA workload only)
-                "traffic": 3.15e9 if (wl == "celeba_d64_gc" and B == 512) else None,
-                "traffic_note": "per step (9 contraction launches); algorithmic operand bytes per step = "
+                # capture in profiles/r1_ncu_full_contraction_kernels_final.txt (B=512/GPU CelebA workload only)
+                "traffic": 2.59e9 if (wl == "celeba_d64_gc" and B == 512) else None,
+                "traffic_note": "per step (8 contraction launches); algorithmic operand bytes per step = "
                                 f"{2 * B * (1032196 if wl == 'celeba_d64_gc' else 4756)}"}
         line = {
             "metric": "per-sample clipped grads/sec (DP D-step)", "value": value, "unit": "samples/s",
