@@ -456,14 +456,21 @@ int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long
   int qpb = (Q + qchunks - 1) / qchunks;
   dim3 grid((Q + qpb - 1) / qpb, B);
   const bool vec4 = sm == 1 && (M % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
-                    (reinterpret_cast<uintptr_t>(src) & 15) == 0 && M / 4 <= 256;
+                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   if (vec4) {
     const int mv = M / 4;
-    int vblock = mv >= 128 ? ((mv + 31) / 32 * 32) : 128;     // at least 128 threads: several positions in parallel
-    if (vblock % mv) vblock = (vblock / mv + 1) * mv;         // whole groups of channel vectors
-    if (vblock > 1024) vblock = mv;
-    cg::stage_xt_vec4_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
-                                                             bias_rows, sumsq, qpb);
+    int vblock = 256;                                         // rows wider than 1024 channels: block-sized strips
+    if (mv <= 256) {
+      vblock = mv >= 128 ? ((mv + 31) / 32 * 32) : 128;       // at least 128 threads: several positions in parallel
+      if (vblock % mv) vblock = (vblock / mv + 1) * mv;       // whole groups of channel vectors
+      if (vblock > 1024) vblock = mv;
+    }
+    if (mv > 256)
+      cg::stage_xt_vec4_wide_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
+                                                                     slot0, bias_rows, sumsq, qpb);
+    else
+      cg::stage_xt_vec4_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
+                                                                      slot0, bias_rows, sumsq, qpb);
   } else {
     cg::stage_xt_kernel<<<grid, block, 0, S(stream)>>>(src, sn, sm, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
                                                        bias_rows, sumsq, qpb);
@@ -494,19 +501,24 @@ int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long
   p.slot_stride = plan->slot_stride;
   p.chunk_stride = plan->slot_stride * n_slots_total;
   const int n_pos = plan->Hs * plan->Ws;
+  const long long extent = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1) * sh +
+                           static_cast<long long>(g->W - 1 + g->KW * g->dw) * sw;
+  if (sc < 0 || sh < 0 || sw < 0 || extent >= (1LL << 31) || plan->slot_stride >= (1LL << 31))
+    return fail("cg_stage_yt: one sample must span fewer than 2^31 elements with non-negative strides");
   const bool vec4 = !plan->merged && sc == 1 && (g->C % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
                     (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-  if (vec4) {
-    // 256 threads = 32 positions per step; 128 positions per block (4 steps, unrolled -> 4 loads in flight)
-    const int ppb = 128;
-    dim3 grid((n_pos + ppb - 1) / ppb, B, n_planes * n_cb);
-    cg::stage_yt_vec4_kernel<<<grid, 256, 0, S(stream)>>>(src, p, dst, ppb);
-  } else {
-    int gx = (n_pos + 63) / 64;                    // 8 warps per block, 8 positions per warp
-    if (gx < 1) gx = 1;
-    dim3 grid(gx, B, n_planes * n_cb);
-    cg::stage_yt_kernel<<<grid, 256, 0, S(stream)>>>(src, p, dst);
+  // threads = 8 lanes per position; small window grids get a block that covers them in k equal steps
+  // (36 positions -> 288 threads x 1 step, 100 -> 416 x 2) instead of idling most of a 256-thread block
+  int threads = 256, ppb = 128;
+  if (n_pos < 128) {
+    int k = 1;
+    while (8 * ((n_pos + k - 1) / k) > 512) ++k;
+    threads = (8 * ((n_pos + k - 1) / k) + 31) / 32 * 32;
+    ppb = n_pos;
   }
+  dim3 grid((n_pos + ppb - 1) / ppb, (B + cg::kYtSamples - 1) / cg::kYtSamples, n_planes * n_cb);
+  if (vec4) cg::stage_yt_kernel<true><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb);
+  else cg::stage_yt_kernel<false><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -403,6 +403,41 @@ __global__ void stage_xt_vec4_kernel(const float* __restrict__ src, long long sn
   }
 }
 
+// Rows wider than 1024 channels with few positions (the 8192-wide Linear input): block-sized strips of
+// channel vectors, every thread walks its strips over the block's positions.
+__global__ void stage_xt_vec4_wide_kernel(const float* __restrict__ src, long long sn, long long sh, long long sw, int M,
+                                          int Wo, int Q, float scale, float* __restrict__ dst, long long rows_total,
+                                          int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq, int qpb) {
+  const int n = blockIdx.y;
+  const int q_lo = blockIdx.x * qpb, q_hi = min(q_lo + qpb, Q);
+  const int mv = M >> 2;
+  float ssq = 0.f;
+  for (int tm = threadIdx.x; tm < mv; tm += blockDim.x) {
+    const int m = 4 * tm;
+    const float* s = src + static_cast<long long>(n) * sn + m;
+    float* d = dst + (static_cast<long long>(m >> 5) * rows_total + static_cast<long long>(slot0 + n) * Q) * 32 + (m & 31);
+    float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = q_lo; q < q_hi; ++q) {
+      const int oh = q / Wo, ow = q - oh * Wo;
+      float4 v = __ldg(reinterpret_cast<const float4*>(s + oh * sh + ow * sw));
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w;
+      ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
+      v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+      *reinterpret_cast<float4*>(d + static_cast<long long>(q) * 32) = v;
+    }
+    if (bias_rows) {
+      float* b = bias_rows + static_cast<long long>(slot0 + n) * M + m;
+      atomicAdd(b, bs.x); atomicAdd(b + 1, bs.y); atomicAdd(b + 2, bs.z); atomicAdd(b + 3, bs.w);
+    }
+  }
+  if (sumsq) {
+    __shared__ float sh_red[32];
+    ssq = block_sum(ssq, sh_red);
+    if (threadIdx.x == 0) atomicAdd(sumsq + slot0 + n, ssq);
+  }
+}
+
 struct YtParams {
   int B, C, H, W;              // source [B][C][H][W] through strides
   long long sn, sc, sh_, sw_;
@@ -416,60 +451,88 @@ struct YtParams {
 };
 
 // Yt[plane*n_cb + c/32][slot][hs][ws][c%32] = tf32(scale * S[n][c][h][w]) (zero outside).
-// grid (position chunks, B, planes*n_cb); a warp writes one 128-byte row and, for channels_last sources,
-// reads one 128-byte row.
-__global__ void stage_yt_kernel(const float* __restrict__ src, const __grid_constant__ YtParams p,
-                                float* __restrict__ dst) {
-  const int n = blockIdx.y;
-  const int pl = blockIdx.z / p.n_cb, chi = blockIdx.z - pl * p.n_cb;
-  const int jh = pl / p.n_rw, jw = pl - jh * p.n_rw;
-  const int lane = threadIdx.x & 31;
-  const int cs = chi * 32 + lane;
-  int c = cs, wk = 0;
-  if (p.merged) { const int kw = cs / p.C; c = cs - kw * p.C; wk = kw * p.dw - p.pw; }
-  const bool c_ok = cs < p.Cs;
-  const float* s = src + static_cast<long long>(n) * p.sn + static_cast<long long>(c) * p.sc;
-  float* d = dst + static_cast<long long>(blockIdx.z) * p.chunk_stride + static_cast<long long>(p.slot0 + n) * p.slot_stride + lane;
-  const int n_pos = p.Hs * p.Ws;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int pos = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pos < n_pos; pos += warps) {
-    const int hs = pos / p.Ws, ws = pos - hs * p.Ws;
-    const int h = p.sth * (hs + p.ah_min) + p.rho_h[jh];
-    const int w = p.merged ? ws * p.stw + wk : p.stw * (ws + p.aw_min) + p.rho_w[jw];
-    float v = 0.f;
-    if (c_ok && h >= 0 && h < p.H && w >= 0 && w < p.W)
-      v = p.scale * s[static_cast<long long>(h) * p.sh_ + static_cast<long long>(w) * p.sw_];
-    d[static_cast<long long>(pos) * 32] = round_tf32(v);
-  }
-}
+// grid (position chunks, B, planes*n_cb).  A lane owns 4 consecutive staged channels of one position and
+// issues ONE 16-byte store, so a warp stages 4 positions (4 x 128-byte chunk rows) per step.
+//   kVec  : channels-fastest, un-merged source with C % 4 == 0 -> one float4 load per lane
+//   !kVec : everything else (merged thin inputs c' = kw*C + c, C % 4 != 0, channel-strided sources) ->
+//           4 scalar gathers through per-lane precomputed offsets
+// These kernels are instruction-issue bound, not DRAM bound (ncu: 1600 warp instructions per 16 stores with
+// 64-bit index arithmetic and a division per position), so all per-position arithmetic is 32-bit and
+// incremental: (hs, ws) advance by a block-uniform (dh, dw) per step.  The host checks that one sample's
+// source extent fits in 31 bits.
+constexpr int kYtSamples = 4;     // samples per block: the same index arithmetic, 4 independent loads in flight
 
-// float4 variant for channels-fastest, un-merged sources with C % 4 == 0: 8 lanes x float4 = one 128-byte
-// chunk row, so a warp stages 4 window positions per step.  grid (position chunks, B, planes*n_cb).
-__global__ void stage_yt_vec4_kernel(const float* __restrict__ src, const __grid_constant__ YtParams p,
-                                     float* __restrict__ dst, int pos_per_block) {
-  const int n = blockIdx.y;
+template <bool kVec>
+__global__ void __launch_bounds__(512)
+stage_yt_kernel(const float* __restrict__ src, const __grid_constant__ YtParams p, float* __restrict__ dst,
+                int pos_per_block) {
+  const int n0 = blockIdx.y * kYtSamples;
   const int pl = blockIdx.z / p.n_cb, chi = blockIdx.z - pl * p.n_cb;
   const int jh = pl / p.n_rw, jw = pl - jh * p.n_rw;
-  const int c = chi * 32 + 4 * (threadIdx.x & 7);
-  const bool c_ok = c < p.Cs;                      // Cs % 4 == 0: a vector is entirely in or out
-  const float* s = src + static_cast<long long>(n) * p.sn + c;
-  float* d = dst + static_cast<long long>(blockIdx.z) * p.chunk_stride + static_cast<long long>(p.slot0 + n) * p.slot_stride +
-             4 * (threadIdx.x & 7);
-  const int n_pos = p.Hs * p.Ws;
+  const int l8 = threadIdx.x & 7;
+  const int sh = static_cast<int>(p.sh_), sw = static_cast<int>(p.sw_), sc = static_cast<int>(p.sc);
+  const int H = p.H, W = p.W, Ws = p.Ws, sth = p.sth, stw = p.stw;
+  const float scale = p.scale;
+  int off[4], wk[4];
+  bool ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cs = chi * 32 + 4 * l8 + j;
+    int c = cs; wk[j] = 0;
+    if (p.merged) { const int kw = cs / p.C; c = cs - kw * p.C; wk[j] = kw * p.dw - p.pw; }
+    ok[j] = cs < p.Cs;
+    off[j] = ok[j] ? c * sc + wk[j] * sw : 0;
+  }
+  const float* s[kYtSamples];
+  float* d[kYtSamples];
+  bool live[kYtSamples];
+#pragma unroll
+  for (int k = 0; k < kYtSamples; ++k) {
+    live[k] = n0 + k < p.B;
+    const int n = live[k] ? n0 + k : n0;
+    s[k] = src + static_cast<long long>(n) * p.sn;
+    d[k] = dst + static_cast<long long>(blockIdx.z) * p.chunk_stride + static_cast<long long>(p.slot0 + n) * p.slot_stride + 4 * l8;
+  }
+  const int h_base = sth * p.ah_min + p.rho_h[jh];
+  const int w_base = p.merged ? 0 : stw * p.aw_min + p.rho_w[jw];      // merged: + wk[j] per channel
+  const int n_pos = p.Hs * Ws;
   const int p_lo = blockIdx.x * pos_per_block, p_hi = min(p_lo + pos_per_block, n_pos);
   const int step = blockDim.x >> 3;
-#pragma unroll 4
-  for (int pos = p_lo + (threadIdx.x >> 3); pos < p_hi; pos += step) {
-    const int hs = pos / p.Ws, ws = pos - hs * p.Ws;
-    const int h = p.sth * (hs + p.ah_min) + p.rho_h[jh];
-    const int w = p.stw * (ws + p.aw_min) + p.rho_w[jw];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c_ok && h >= 0 && h < p.H && w >= 0 && w < p.W) {
-      v = __ldg(reinterpret_cast<const float4*>(s + static_cast<long long>(h) * p.sh_ + static_cast<long long>(w) * p.sw_));
-      v.x = round_tf32(v.x * p.scale); v.y = round_tf32(v.y * p.scale);
-      v.z = round_tf32(v.z * p.scale); v.w = round_tf32(v.w * p.scale);
+  const int dh = step / Ws, dw = step - dh * Ws;
+  int pos = p_lo + (threadIdx.x >> 3);
+  int hs = pos / Ws, ws = pos - hs * Ws;
+  for (; pos < p_hi; pos += step) {
+    const int h = sth * hs + h_base, w0 = stw * ws + w_base;
+    const bool h_ok = h >= 0 && h < H;
+    const int base = h * sh + w0 * sw;
+    float4 v[kYtSamples];
+    if (kVec) {
+      const bool in = ok[0] && h_ok && w0 >= 0 && w0 < W;
+#pragma unroll
+      for (int k = 0; k < kYtSamples; ++k)
+        v[k] = in ? __ldg(reinterpret_cast<const float4*>(s[k] + base + off[0])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      bool in[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int w = w0 + wk[j]; in[j] = ok[j] && h_ok && w >= 0 && w < W; }
+#pragma unroll
+      for (int k = 0; k < kYtSamples; ++k) {
+        v[k].x = in[0] ? __ldg(s[k] + base + off[0]) : 0.f;
+        v[k].y = in[1] ? __ldg(s[k] + base + off[1]) : 0.f;
+        v[k].z = in[2] ? __ldg(s[k] + base + off[2]) : 0.f;
+        v[k].w = in[3] ? __ldg(s[k] + base + off[3]) : 0.f;
+      }
     }
-    *reinterpret_cast<float4*>(d + static_cast<long long>(pos) * 32) = v;
+#pragma unroll
+    for (int k = 0; k < kYtSamples; ++k) {
+      if (!live[k]) continue;
+      float4 o;
+      o.x = round_tf32(v[k].x * scale); o.y = round_tf32(v[k].y * scale);
+      o.z = round_tf32(v[k].z * scale); o.w = round_tf32(v[k].w * scale);
+      *reinterpret_cast<float4*>(d[k] + pos * 32) = o;
+    }
+    ws += dw; hs += dh;
+    if (ws >= Ws) { ws -= Ws; ++hs; }
   }
 }
 
