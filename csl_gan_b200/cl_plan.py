@@ -246,8 +246,7 @@ class ClLayerPlan:
             n_nt = (n_taps + tpt - 1) // tpt
         n_tiles = ((self.M + 127) // 128) * n_nt
         units = (slot_hi - slot_lo) * max(1, self.Q // 32) if self.Q >= 32 else (slot_hi - slot_lo + 32 // self.Q - 1) // (32 // self.Q)
-        want = max(1, (2 * sm_count) // max(1, n_tiles))
-        n_groups = max(1, min(want, units // 4 if units >= 4 else 1))
+        n_groups = _pick_split_k(n_tiles, units, sm_count)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SPLITK, n_groups, slot_lo, slot_hi
         # where does the gradient-natural layout T[m][tap][c'] already equal the parameter's memory?
         natural = None
@@ -314,6 +313,22 @@ class ClLayerPlan:
         d.epi, d.out, d.out_group_stride = L.EPI_STORE, L.ptr(out), w.numel()
         L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
         return out
+
+
+def _pick_split_k(n_tiles: int, units: int, sm_count: int) -> int:
+    """Split-K group count for the clipped-sum GEMM: items = n_tiles * groups are dealt round-robin to one
+    persistent CTA per SM, so what matters is how full the last wave is (100 tiles x 2 groups on 148 SMs is
+    1.35 waves = 68 % busy; x 10 groups is 6.76 waves = 96.5 %).  Every group costs one more split-K epilogue
+    (a 128 x N tile of `red.add`) per tile, hence the small per-group penalty and the floor of 8 k-blocks."""
+    g_max = max(1, min(64, units // 8 if units >= 8 else 1))
+    best, best_score = 1, -1.0
+    for g in range(1, g_max + 1):
+        items = n_tiles * g
+        waves = -(-items // sm_count)
+        score = items / (waves * sm_count) - 0.004 * g
+        if score > best_score + 1e-9:
+            best, best_score = g, score
+    return best
 
 
 def layer_bias_len(layer: nn.Module, kind: str) -> int:
