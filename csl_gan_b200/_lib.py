@@ -50,7 +50,7 @@ class ClDesc(C.Structure):
                 ("Yt", C.c_void_p), ("n_slots_total", C.c_int),
                 ("group_mode", C.c_int), ("n_groups", C.c_int), ("slot_lo", C.c_int), ("slot_hi", C.c_int),
                 ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong), ("max_ctas", C.c_int),
-                ("n_seg", C.c_int), ("seg_stride", C.c_int)]
+                ("n_seg", C.c_int), ("seg_stride", C.c_int), ("pair", C.c_int)]
 
 
 class GhostDesc(C.Structure):
@@ -96,6 +96,7 @@ _PROTOS = {
                               C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p]),
     "cg_cl_contract": (C.c_int, [C.POINTER(ClDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
+    "cg_cl_pair_ok": (C.c_int, [C.c_int, C.POINTER(UnfoldGeom), C.POINTER(GhostPlan)]),
     "cg_rowpair_dot": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                  C.c_void_p]),
     "cg_joint_rows_sumsq": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -131,7 +132,8 @@ EXPORTED_SYMBOLS = tuple(_PROTOS)
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
-_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost", "cg_plan_cl"}
+_NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost", "cg_plan_cl",
+              "cg_cl_pair_ok"}
 
 
 def load() -> C.CDLL:
@@ -188,6 +190,11 @@ def call(name: str, *args):
         raise CslGanCudaError(f"{name}: {lib.cg_last_error().decode(errors='replace')}")
     if launching:
         launch_count += 1
+
+
+def cl_pair_ok(M: int, geom, plan) -> bool:
+    """May cg_cl_contract run this layer's clipped sum on CTA pairs (cg_cl_desc.pair = 1)?"""
+    return bool(load().cg_cl_pair_ok(int(M), C.byref(geom), C.byref(plan)))
 
 
 def stream_ptr(device=None) -> int:

@@ -9,6 +9,8 @@ Replaces the same fork operations as the legacy plan (upstream opacus `_capture_
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional
 
@@ -105,6 +107,10 @@ class ClLayerPlan:
         self.thin = (self.kind != "linear" and not self.ghost and self.Q >= 256 and M * self.ldT <= 16384)
         self.Gs = torch.zeros((S, M * self.ldT), device=dev) if self.thin else None
         self._gs_joint = 1
+        # clipped-sum GEMM on CTA pairs (cta_group::2) where the layer is wide enough; CSLGAN_NO_PAIR=1 is the
+        # A/B switch for measurements
+        self.pair = (not self.thin and os.environ.get("CSLGAN_NO_PAIR", "0") != "1"
+                     and L.cl_pair_ok(M, self.geom, self.plan))
         if self.kind == "convT" and self.b_idx is not None:
             self._bias_scratch = torch.empty((_round_up(self.bias_len, 32) // 32, Bpad * H * W, 32), device=dev)
             self._HW = (H, W)
@@ -246,7 +252,13 @@ class ClLayerPlan:
             n_nt = (n_taps + tpt - 1) // tpt
         n_tiles = ((self.M + 127) // 128) * n_nt
         units = (slot_hi - slot_lo) * max(1, self.Q // 32) if self.Q >= 32 else (slot_hi - slot_lo + 32 // self.Q - 1) // (32 // self.Q)
-        n_groups = _pick_split_k(n_tiles, units, sm_count)
+        if self.pair:
+            # CTA pairs: 256 x 256 tiles (two half tiles of one tap x four chunks), one pair per two SMs
+            n_tiles = (self.M // 256) * ((n_taps * (n_cb // 4) + 1) // 2)
+            n_groups = _pick_split_k(n_tiles, units, sm_count // 2)
+        else:
+            n_groups = _pick_split_k(n_tiles, units, sm_count)
+        d.pair = 1 if self.pair else 0
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SPLITK, n_groups, slot_lo, slot_hi
         # where does the gradient-natural layout T[m][tap][c'] already equal the parameter's memory?
         natural = None

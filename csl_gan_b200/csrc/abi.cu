@@ -11,6 +11,7 @@
 #include "contract.cuh"
 #include "ghost.cuh"
 #include "cl.cuh"
+#include "cl_pair.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -140,6 +141,65 @@ void axis_plan(int K, int s, int d, int pad, int* a, int* j_of, int* rho, int* n
     if (j < 0) { j = *n_rho; rho[(*n_rho)++] = rr; }
     j_of[k] = j;
   }
+}
+
+// CTA-pair launch of the split-K clipped sum (cl_pair.cuh); `p` is the single-CTA parameter block already filled
+int launch_pair(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, const cg::ClParams& p,
+                int kb_w, int kb_h, int kb_s, cg_stream_t stream) {
+  (void)g;
+  cg::ClPairParams q;
+  memset(&q, 0, sizeof(q));
+  q.M = d->M; q.n_mp = d->M / 256;
+  q.C = p.C; q.n_cb = p.n_cb; q.n_taps = p.n_taps;
+  q.hpt = p.n_cb / 4; q.n_ht = p.n_taps * q.hpt; q.n_nt = (q.n_ht + 1) / 2;
+  for (int t = 0; t < p.n_taps; ++t) { q.tap_plane[t] = p.tap_plane[t]; q.tap_hoff[t] = p.tap_hoff[t]; q.tap_woff[t] = p.tap_woff[t]; }
+  q.Q = p.Q; q.Wo = p.Wo; q.kb_s = p.kb_s; q.nkb_slot = p.nkb_slot;
+  q.oob_chunk = plan->n_rh * plan->n_rw * p.n_cb;
+  q.u_lo = p.u_lo; q.u_hi = p.u_hi; q.upg = p.upg; q.n_groups = p.n_groups;
+  q.out = p.out; q.ldT = p.ldT;
+  q.n_items = static_cast<long long>(q.n_groups) * q.n_nt * q.n_mp;
+  CUtensorMap tx, ty;
+  {
+    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->M + 31) / 32)};
+    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
+    cuuint32_t box[3] = {32, 32, 4};
+    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  }
+  {
+    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                          static_cast<cuuint64_t>(d->n_slots_total),
+                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * p.n_cb};
+    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
+                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
+    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(kb_w), static_cast<cuuint32_t>(kb_h),
+                         static_cast<cuuint32_t>(kb_s), 4};
+    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  }
+  DevInfo dv;
+  if (dev_info(&dv)) return 1;
+  static int max_pairs[64] = {0};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!max_pairs[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::cl_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kPairSmemBytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (dv.sm / 2)); cfg.blockDim = dim3(cg::kClThreads); cfg.dynamicSmemBytes = cg::kPairSmemBytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    CG_CHECK(cudaOccupancyMaxActiveClusters(&n, cg::cl_pair_kernel, &cfg));
+    if (n < 1) return fail("cl_pair_kernel: no CTA pair can be resident on this device");
+    max_pairs[dev] = n;
+  }
+  long long pairs = max_pairs[dev];
+  if (d->max_ctas > 0 && d->max_ctas / 2 < pairs) pairs = d->max_ctas / 2 > 0 ? d->max_ctas / 2 : 1;
+  if (pairs > q.n_items) pairs = q.n_items;
+  cg::cl_pair_kernel<<<static_cast<int>(2 * pairs), cg::kClThreads, cg::kPairSmemBytes, S(stream)>>>(tx, ty, q);
+  CG_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -523,6 +583,12 @@ int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long
   return 0;
 }
 
+int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan) {
+  if (!g || !plan) return 0;
+  const int n_cb = plan->Cp / 32;
+  return (M >= 256 && M % 256 == 0 && n_cb >= 4 && n_cb % 4 == 0 && !plan->merged) ? 1 : 0;
+}
+
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream) {
   if (!d || !g || !plan) return fail("null argument");
   DevInfo dv;
@@ -578,6 +644,12 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   p.ldT = static_cast<long long>(p.n_taps) * p.C;
   p.KH = g->KH; p.KW = g->KW; p.Corig = g->C; p.merged = plan->merged;
   p.n_items = static_cast<long long>(p.n_groups) * p.n_nt * p.n_mtiles;
+
+  if (d->pair) {
+    if (!cg_cl_pair_ok(d->M, g, plan) || d->group_mode != CG_GROUP_SPLITK || d->epi != CG_EPI_ACCUM || kb_rows != 32)
+      return fail("cg_cl_contract: pair = 1 needs a split-K clipped sum with M %% 256 == 0 and 128-channel multiples");
+    return launch_pair(d, g, plan, p, kb_w, kb_h, kb_s, stream);
+  }
 
   CUtensorMap tx, ty;
   {

@@ -225,7 +225,13 @@ typedef struct cg_cl_desc {
   int max_ctas;
   int n_seg, seg_stride;       /* CG_GROUP_SAMPLE: a group also covers slots slot_lo+g + s*seg_stride, s < n_seg
                                   (per-sample sum over passes, accum_passes=True); 0/1 = single slot       */
+  int pair;                    /* 1: run on CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles, each CTA
+                                  loads half of the unfolded operand).  Only CG_GROUP_SPLITK + CG_EPI_ACCUM with
+                                  M % 256 == 0 and 128-channel multiples (cg_cl_pair_ok); an error otherwise */
 } cg_cl_desc;
+
+/* 1 when cg_cl_contract accepts d->pair = 1 for this layer (split-K clipped sum), else 0 */
+int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan);
 
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream);
 

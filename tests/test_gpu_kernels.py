@@ -94,7 +94,8 @@ def _conv_case(B, Cin, Cout, H, W, k, s, p, d=1, seed=0):
 @pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p,d", [
     (3, 3, 64, 64, 64, 5, 2, 2, 1),      # D64 blocks.0
     (2, 64, 128, 32, 32, 5, 2, 2, 1),    # D64 blocks.1
-    (2, 256, 512, 8, 8, 5, 2, 2, 1),     # D64 blocks.3 (Q = 16 < one k-block)
+    (2, 128, 256, 16, 16, 5, 2, 2, 1),   # D64 blocks.2 (clipped sum on CTA pairs, odd number of half tiles)
+    (2, 256, 512, 8, 8, 5, 2, 2, 1),     # D64 blocks.3 (Q = 16 < one k-block; CTA pairs, two 256-row tile pairs)
     (3, 1, 64, 28, 28, 5, 2, 2, 1),      # MNIST DCRN blocks.0 (Q = 196, ragged k tail)
     (2, 64, 128, 14, 14, 5, 2, 2, 1),    # MNIST DCRN blocks.1 (Q = 49)
     (2, 5, 7, 9, 11, 3, 1, 1, 1),        # stride 1
@@ -144,6 +145,40 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d,
     torch.cuda.synchronize()
     ref = torch.einsum("n,n...->...", f[:B].cpu(), gw_ref)
     assert ((out.cpu() - ref).norm() / ref.norm()).item() < 1e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p", [
+    (40, 128, 256, 16, 16, 5, 2, 2),     # Q = 64: 80 k-blocks, 13 tile pairs (the last one half empty)
+    (70, 256, 512, 8, 8, 3, 1, 1),       # Q = 64, 3x3 stride 1: 18 half tiles, two 256-row pairs
+    (33, 384, 256, 4, 4, 5, 2, 2),       # Q = 4: 8 samples per k-block, ragged last k-block, 3 half tiles per tap
+])
+def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, W, k, s, p):
+    """cl_pair_kernel (cluster of 2, tcgen05 cta_group::2) vs cl_contract_kernel vs the oracle, split-K over
+    several groups so the pipeline wraps and both accumulator stages are used."""
+    from csl_gan_b200.grad_sample import LayerPlan
+    conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p, 1, seed=3)
+    gw_ref, _ = O.conv2d_grad_sample(conv, A, Bp)
+    conv = conv.to(DEV)
+    plan = LayerPlan("conv", conv, 0, 1)
+    Bpad = (B + 31) // 32 * 32
+    plan.capture_activation(A.to(DEV).contiguous(memory_format=torch.channels_last), 0, Bpad, 1)
+    plan.capture_backprop(Bp.to(DEV).contiguous(memory_format=torch.channels_last), 0, 1.0)
+    assert plan.impl is not None and plan.impl.pair
+    f = torch.rand(Bpad, device=DEV) + 0.25
+    f[B:] = 0
+    plan.scale_backprops(f, 0, Bpad)
+    ref = torch.einsum("n,n...->...", f[:B].cpu(), gw_ref)
+    outs = {}
+    for pair in (True, False):
+        plan.impl.pair = pair
+        for sms in (148, 6):                       # many groups / few CTAs (persistent loop over items)
+            out = torch.empty_like(conv.weight)
+            plan.weighted_sum(out, 0, B, sms, accumulate=False, factor_row=f)
+            torch.cuda.synchronize()
+            outs[(pair, sms)] = out.cpu()
+            assert ((out.cpu() - ref).norm() / ref.norm()).item() < 1e-3, (pair, sms)
+    # same TF32 products, different summation order only
+    assert ((outs[(True, 148)] - outs[(False, 148)]).norm() / ref.norm()).item() < 1e-5
 
 
 @pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p", [
