@@ -85,6 +85,10 @@ class DiscriminatorStep:
         self.public_batch = public_batch
         self.collect_stats = collect_stats
         self.skip_weight_grads = skip_weight_grads
+        # a channels_last critic converts every NCHW batch it is given (and the capture kernels would convert it
+        # once more): do it once, up front
+        self._nhwc = any(p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last)
+                         for p in D.parameters())
 
     # ------------------------------------------------------------------ losses (train.py:342-358)
     def _fake_loss(self, fake_img, y):
@@ -150,9 +154,15 @@ class DiscriminatorStep:
         use_gc = opt.dp_mode == "gc" and use_dp
         use_is = opt.dp_mode == "is" and use_dp
         fake_img = fake_img.detach()
+        if self._nhwc and img.dim() == 4:
+            img = img.contiguous(memory_format=torch.channels_last)
+            fake_img = fake_img.contiguous(memory_format=torch.channels_last)
 
         if opt.per_sample_grad and use_dp:
-            eng.enable_hooks()
+            if use_gc and self.skip_weight_grads:
+                eng.enable_hooks(freeze_weights=True)     # backward = dgrad chain only (privacy_engine.enable_hooks)
+            else:
+                eng.enable_hooks()
         if use_is:
             img = img.detach().requires_grad_(True)
         if use_gc and opt.grad_clip_mode[:8] == "adaptive":

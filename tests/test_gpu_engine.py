@@ -247,6 +247,37 @@ def test_smaller_last_batch_and_engine_reuse_across_steps(name, sizes):
     assert eng.steps == len(sizes)
 
 
+@pytest.mark.parametrize("name", ["mnist", "d48"])
+def test_frozen_weights_backward_matches_plain_backward(name):
+    """enable_hooks(freeze_weights=True) + engine.backward(loss) (dgrad chain only, no weight gradients) stages
+    exactly the same per-sample operands as the reference-style loss.backward(); requires_grad is restored."""
+    D, shape, ncls, lo = make(name)
+    B = 6
+    real, fake, y = batch(shape, ncls, lo, B, seed=21)
+    real, fake, y = real.to(DEV), fake.to(DEV), (y.to(DEV) if y is not None else None)
+    outs = {}
+    for mode in ("plain", "inputs", "frozen"):
+        Dg = copy.deepcopy(D).to(DEV)
+        eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=1000, noise_multiplier=0.0, max_grad_norm=0.3,
+                               num_private_passes=1, auto_clip_and_accum_on_step=False)
+        eng.enable_hooks(freeze_weights=(mode == "frozen"))
+        if mode == "frozen":
+            assert not any(p.requires_grad for p in Dg.parameters())
+        loss = d_loss(Dg, real, fake, y)
+        loss.backward() if mode == "plain" else eng.backward(loss)
+        eng.disable_hooks()
+        assert all(p.requires_grad for p in Dg.parameters())
+        if mode != "plain":
+            assert all(p.grad is None for p in Dg.parameters())          # no batch-summed weight gradients formed
+        norms = eng.per_sample_norms().clone()
+        outs[mode] = (norms, [c.clone() for c in eng.clip()])
+        eng.accumulate_batch()
+    for mode in ("inputs", "frozen"):
+        assert torch.allclose(outs[mode][0], outs["plain"][0], rtol=1e-5, atol=1e-8)
+        for a, b in zip(outs[mode][1], outs["plain"][1]):
+            assert rel(a, b) < 1e-5
+
+
 def test_lazy_grad_sample_view_and_materialize():
     D, shape, ncls, lo = make("mnist_dcrn")
     B = 5
