@@ -282,11 +282,26 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's ORIGINAL stdout; fd 1 itself is pointed at stderr for the rest
+    of the run so that library chatter (NCCL prints its version banner on stdout) cannot end up next to it."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -334,9 +349,9 @@ def main():
         eng.accumulate_batch()
         eng.step()
 
-    # single GPU: the DP machinery is captured once into a CUDA graph and replayed (launch-bound at MNIST sizes);
-    # with several ranks it stays eager because engine.step() issues the NCCL allreduce from Python
-    use_graph = not args.no_graph and not dist_on
+    # the DP machinery is captured once into a CUDA graph and replayed (launch-bound at MNIST sizes); with several
+    # ranks the graph contains the NCCL allreduce of engine.step() (CSLGAN_GRAPH_DIST=0 keeps multi-rank runs eager)
+    use_graph = not args.no_graph and (not dist_on or os.environ.get("CSLGAN_GRAPH_DIST", "1") == "1")
     launches0 = L.launch_count
     dp_only()
     launches = L.launch_count - launches0                                       # ABI launch calls per step
@@ -394,8 +409,7 @@ def main():
             staged["ev"].record(copy_stream)
 
     upload()
-    # one CUDA graph for the whole step (critic fwd/bwd, capture, norms, clip, noise, Adam) on a single GPU;
-    # with several ranks the step stays eager (the NCCL allreduce is issued from Python)
+    # one CUDA graph for the whole step (critic fwd/bwd, capture, norms, clip, allreduce, noise, Adam)
     runner = None
     if use_graph:
         from csl_gan_b200.dstep import GraphedDiscriminatorStep
@@ -469,8 +483,17 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": f"full DP D-step of the CPU oracle, B={Bc}, 3 timed steps after 1 warm-up "
                                               f"({ms:.0f} ms/step); compare with e2e"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist_on:
+        # CUDA graphs that hold NCCL kernels must be gone before the communicator is torn down; even so NCCL's
+        # teardown was seen to hang after graph replays, so the ranks synchronise and leave without it
+        runner = dp_graph = None
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        if use_graph:
+            os._exit(0)
         torch.distributed.destroy_process_group()
 
 
