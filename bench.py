@@ -231,6 +231,56 @@ def bandwidth_kernels(hbm_peak_gbs):
     return out
 
 
+def other_configs(dev):
+    """BASELINE.json configs[1..3] through the public API (DiscriminatorStep, eager, inputs resident on the
+    device): MNIST dp_mode=is, CelebA gc adaptive-pl with mean samples, CelebA is per-parameter with gradient
+    penalty.  Reported as samples/s of the private batch; parity for these paths is in tests/."""
+    from csl_gan_b200 import discriminators as DD
+    from csl_gan_b200 import options as OPT
+    from csl_gan_b200.dstep import DiscriminatorStep, setup_privacy_engine
+    out = {}
+    cases = {
+        "mnist_is_bs600": (["MNIST", "--conditional", "--dp_mode", "is", "--sigma", "10"], 600),
+        "celeba_gc_adaptive_pl_bs128": (["CelebA", "-nms", "32", "--dp_mode", "gc", "-gcm", "adaptive-pl"], 128),
+        "celeba_is_per_param_gp_bs128": (["CelebA", "-nms", "32", "--dp_mode", "is", "-ispp", "True"], 128),
+    }
+    for name, (argv, B) in cases.items():
+        o = OPT.parse(argv + ["-bs", str(B), "-tss", "180000", "--manual_seed", "3"])
+        ncls = o.n_classes if o.conditional else 0
+        D = DD.build_discriminator(o.dataset, o.model, n_classes=ncls, im_size=o.im_size, emb_mode=o.d_label_emb_mode,
+                                   conditional_arch=o.conditional_arch, aux_loss_type=o.aux_loss_type,
+                                   aux_loss_scalar=o.aux_loss_scalar, weights_seed=o.weights_seed, device=dev)
+        shape = (1, 28, 28) if o.dataset == "MNIST" else (3, o.im_size, o.im_size)
+        if o.dataset == "CelebA":
+            D = D.to(memory_format=torch.channels_last)
+        opt_d = torch.optim.Adam(D.parameters(), lr=o.d_lr, betas=(o.adam_b1, o.adam_b2))
+        eng = setup_privacy_engine(o, D, opt_d)
+        g = torch.Generator().manual_seed(0)
+        real = torch.rand((B,) + shape, generator=g).to(dev) * 2 - 1
+        fake = torch.rand((B,) + shape, generator=g).to(dev) * 2 - 1
+        y = torch.randint(0, ncls, (B,), generator=g).to(dev) if ncls else None
+        pub = torch.rand((B,) + shape, generator=g).to(dev) * 0.5
+
+        def public_batch(n, labels, pub=pub, y=y):
+            return pub[:n], (labels if labels is not None else y)
+
+        step = DiscriminatorStep(o, D, opt_d, eng, public_batch=public_batch)
+        for _ in range(3):
+            step(real, y, fake, y, use_dp=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_it = 10
+        e0.record()
+        for _ in range(n_it):
+            step(real, y, fake, y, use_dp=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_it
+        out[name] = {"argv": " ".join(argv), "batch": B, "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
+                     "mode": "eager DiscriminatorStep, device-resident inputs"}
+    return out
+
+
 def cpu_step_rate(workload: str, B: int, steps: int, warmup: int):
     """Full DP D-step of the CPU oracle (fwd fake+real, backward with grad-sample hooks, norms, clip,
     weighted sum, accumulate, noise) on all host cores; returns (samples/s, ms/step, cores)."""
@@ -478,6 +528,7 @@ def main():
         }
         if not args.no_extras and world == 1:
             line["bandwidth_kernels"] = bandwidth_kernels(peaks.get("hbm_gbs"))
+            line["other_configs"] = other_configs(dev)
             Bc = 64 if wl == "celeba_d64_gc" else 600
             rate, ms, cores = cpu_step_rate(wl, Bc, 3, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",

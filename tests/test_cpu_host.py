@@ -200,3 +200,21 @@ def test_device_mean_sampler_shapes_and_privacy_cost():
     assert eps > 0
     one = DeviceMeanSampler(torch.rand(1, 4, 1, 8, 8), 0.2, 100, 1000)
     assert one.sample(9)[1] is None
+
+
+def test_split_k_group_count_keeps_the_last_wave_full():
+    """cl_plan._pick_split_k: items = tiles x groups are dealt to one persistent CTA (or CTA pair) per SM (pair)."""
+    from csl_gan_b200.cl_plan import _pick_split_k
+    for n_tiles, units, ctas in ((100, 512, 148), (26, 2048, 148), (7, 8192, 148), (13, 2048, 74), (50, 512, 74),
+                                 (1, 32, 148), (3, 5, 148), (1000, 64, 148)):
+        g = _pick_split_k(n_tiles, units, ctas)
+        assert 1 <= g <= max(1, units // 8)                      # at least 8 k-blocks per group
+        items = n_tiles * g
+        waves = -(-items // ctas)
+        eff = items / (waves * ctas)
+        # never worse than the old rule (about two items per CTA) by more than the per-group penalty
+        g_old = max(1, min((2 * ctas) // n_tiles, units // 4 if units >= 4 else 1))
+        items_old = n_tiles * g_old
+        eff_old = items_old / (-(-items_old // ctas) * ctas)
+        assert eff >= eff_old - 0.004 * 64, (n_tiles, units, ctas, g, eff, eff_old)
+    assert _pick_split_k(100, 512, 148) >= 4                     # the 4x4 layer of the CelebA critic: 1.35 waves before
