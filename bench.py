@@ -231,13 +231,14 @@ def bandwidth_kernels(hbm_peak_gbs):
     return out
 
 
-def other_configs(dev):
+def other_configs(dev, only=None):
     """BASELINE.json configs[1..3] through the public API (DiscriminatorStep, eager, inputs resident on the
     device): MNIST dp_mode=is, CelebA gc adaptive-pl with mean samples, CelebA is per-parameter with gradient
     penalty.  Reported as samples/s of the private batch; parity for these paths is in tests/."""
     from csl_gan_b200 import discriminators as DD
     from csl_gan_b200 import options as OPT
     from csl_gan_b200.dstep import DiscriminatorStep, setup_privacy_engine
+    torch.backends.cudnn.benchmark = True
     out = {}
     cases = {
         "mnist_is_bs600": (["MNIST", "--conditional", "--dp_mode", "is", "--sigma", "10"], 600),
@@ -245,6 +246,8 @@ def other_configs(dev):
         "celeba_is_per_param_gp_bs128": (["CelebA", "-nms", "32", "--dp_mode", "is", "-ispp", "True"], 128),
     }
     for name, (argv, B) in cases.items():
+        if only is not None and name not in only:
+            continue
         o = OPT.parse(argv + ["-bs", str(B), "-tss", "180000", "--manual_seed", "3"])
         ncls = o.n_classes if o.conditional else 0
         D = DD.build_discriminator(o.dataset, o.model, n_classes=ncls, im_size=o.im_size, emb_mode=o.d_label_emb_mode,
@@ -253,7 +256,7 @@ def other_configs(dev):
         shape = (1, 28, 28) if o.dataset == "MNIST" else (3, o.im_size, o.im_size)
         if o.dataset == "CelebA":
             D = D.to(memory_format=torch.channels_last)
-        opt_d = torch.optim.Adam(D.parameters(), lr=o.d_lr, betas=(o.adam_b1, o.adam_b2))
+        opt_d = torch.optim.Adam(D.parameters(), lr=o.d_lr, betas=(o.adam_b1, o.adam_b2), capturable=True)
         eng = setup_privacy_engine(o, D, opt_d)
         g = torch.Generator().manual_seed(0)
         real = torch.rand((B,) + shape, generator=g).to(dev) * 2 - 1
@@ -278,6 +281,24 @@ def other_configs(dev):
         ms = e0.elapsed_time(e1) / n_it
         out[name] = {"argv": " ".join(argv), "batch": B, "ms_per_step": ms, "samples_per_s": B / (ms * 1e-3),
                      "mode": "eager DiscriminatorStep, device-resident inputs"}
+        # the same step as one CUDA graph (these small-batch steps are launch-latency bound)
+        try:
+            from csl_gan_b200.dstep import GraphedDiscriminatorStep
+            runner = GraphedDiscriminatorStep(step, (real, y, fake, y), warmup=2)
+            for _ in range(3):
+                runner(real, y, fake, y)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_it):
+                runner(real, y, fake, y)
+            e1.record()
+            torch.cuda.synchronize()
+            msg = e0.elapsed_time(e1) / n_it
+            out[name]["graph_ms_per_step"] = msg
+            out[name]["graph_samples_per_s"] = B / (msg * 1e-3)
+        except Exception as exc:                      # a step with a host read cannot be captured: report why
+            out[name]["graph_error"] = f"{type(exc).__name__}: {exc}"[:200]
+            torch.cuda.synchronize()
     return out
 
 

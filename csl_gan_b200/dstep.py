@@ -113,6 +113,8 @@ class DiscriminatorStep:
         for p in self.D.parameters():
             p.grad = None
         img, labels = self.public_batch(opt.batch_size, None)
+        if self._nhwc and img.dim() == 4:
+            img = img.contiguous(memory_format=torch.channels_last)
         loss = 0
         if not opt.grad_clip_split:
             _, fl, fa = self._fake_loss(fake_img, fake_y)
@@ -192,6 +194,8 @@ class DiscriminatorStep:
             pen_real, pen_labels = img, labels
             if opt.penalty_use_public_data and self.public_batch is not None:
                 pen_real, pen_labels = self.public_batch(batch_size, labels)
+                if self._nhwc and pen_real.dim() == 4:
+                    pen_real = pen_real.contiguous(memory_format=torch.channels_last)
             if use_dp and opt.per_sample_grad:
                 if not opt.penalty_use_public_data:
                     raise NotImplementedError(
