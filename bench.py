@@ -402,7 +402,7 @@ def main():
     real_pin, fake_pin = real_h.pin_memory(), fake_h.pin_memory()
     y_dev = None if y_h is None else y_h.to(dev)
     opt_d = torch.optim.Adam(D.parameters(), lr=1e-4, betas=(0.0, 0.9) if wl == "celeba_d64_gc" else (0.9, 0.999),
-                             capturable=True)
+                             capturable=True, fused=os.environ.get("CSLGAN_FUSED_ADAM", "1") == "1")
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=cfg["sample_size"], noise_multiplier=cfg["sigma"],
                            max_grad_norm=cfg["C"], accum_passes=False, num_private_passes=1,
                            auto_clip_and_accum_on_step=False, data_parallel=dist_on)
@@ -539,7 +539,8 @@ def main():
                              else "working set fits in L2; MNIST is launch-latency bound (SURVEY.md §8d)"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "mode": "cuda-graph replay of DiscriminatorStep" if use_graph else "eager DiscriminatorStep"},
+                    "mode": "cuda-graph replay of DiscriminatorStep" if use_graph else "eager DiscriminatorStep",
+                    "optimizer": "torch.optim.Adam(capturable=True, fused=%s)" % (os.environ.get("CSLGAN_FUSED_ADAM", "1") == "1")},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "launch_mode": "cuda-graph replay" if use_graph else "eager",
