@@ -1,6 +1,7 @@
 // extern "C" entry points of libcslgan_b200.so (see include/cslgan_b200.h for the contract).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -10,6 +11,7 @@
 #include "../../include/cslgan_b200.h"
 #include "contract.cuh"
 #include "ghost.cuh"
+#include "ghost2.cuh"
 #include "cl.cuh"
 #include "cl_pair.cuh"
 #include "kernels.cuh"
@@ -449,6 +451,43 @@ int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghos
     cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
     cuuint32_t box[3] = {32, 128, 1};
     if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box)) return 1;
+  }
+  const int npos = plan->Hs * plan->Ws;
+  static const bool force_v1 = [] { const char* e = getenv("CSLGAN_GHOST_V1"); return e && e[0] == '1'; }();
+  if (npos <= 128 && plan->Ws <= 256 && plan->Hs <= 256 && !force_v1) {
+    // Gram of the un-shifted planes + tap gather in the epilogue (ghost2.cuh)
+    cg::Ghost2Params q;
+    memset(&q, 0, sizeof(q));
+    q.Q = Q; q.ns = 128 / Q; q.Wo = g->Wo; q.O = d->O; q.C = g->C;
+    q.n_planes = plan->n_rh * plan->n_rw; q.Hs = plan->Hs; q.Ws = plan->Ws; q.npos = npos;
+    q.spp = 128 / npos < q.ns ? 128 / npos : q.ns;
+    q.n_sub = (q.ns + q.spp - 1) / q.spp;
+    int n = 0;
+    for (int pl = 0; pl < q.n_planes; ++pl) {
+      q.plane_tap0[pl] = n;
+      for (int t = 0; t < g->KH * g->KW; ++t)
+        if (plan->tap_plane[t] == pl) q.tap_shift[n++] = plan->tap_hoff[t] * plan->Ws + plan->tap_woff[t];
+    }
+    q.plane_tap0[q.n_planes] = n;
+    q.slot0 = d->slot0; q.n_slots = d->n_slots; q.n_items = p.n_items; q.norm2 = d->norm2;
+    {
+      const cuuint64_t n_cb = (g->C + 31) / 32;
+      cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                            static_cast<cuuint64_t>(d->n_slots_total),
+                            static_cast<cuuint64_t>(q.n_planes) * n_cb};
+      cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
+                           static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
+      cuuint32_t box[5] = {32, static_cast<cuuint32_t>(plan->Ws), static_cast<cuuint32_t>(plan->Hs),
+                           static_cast<cuuint32_t>(q.spp), 1};
+      if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box)) return 1;
+    }
+    const int smem = cg::g2_smem_bytes(Q);
+    CG_CHECK(cudaFuncSetAttribute(cg::ghost2_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid2 = d->max_ctas > 0 ? d->max_ctas : dv.sm;
+    if (grid2 > q.n_items) grid2 = q.n_items;
+    cg::ghost2_norm_kernel<<<grid2, cg::kG2Threads, smem, S(stream)>>>(tx, ty, q);
+    CG_LAUNCH_CHECK();
+    return 0;
   }
   {
     const cuuint64_t n_cb = (g->C + 31) / 32;
