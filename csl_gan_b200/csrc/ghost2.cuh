@@ -239,10 +239,15 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
               float v[16];
               tmem_ld16(lane_addr + static_cast<uint32_t>(256 + pa * 128 + c0), v);
               if (r < rows) {
+                if (c0 >= mylo && c0 + 16 <= myhi) {                // interior chunk: no per-element predicates
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int c = c0 + j;
-                  if (c >= mylo && c < myhi) sts_f32(prow_w + 4u * static_cast<uint32_t>(c), v[j]);
+                  for (int j = 0; j < 16; ++j) sts_f32(prow_w + 4u * static_cast<uint32_t>(c0 + j), v[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
+                    if (c >= mylo && c < myhi) sts_f32(prow_w + 4u * static_cast<uint32_t>(c), v[j]);
+                  }
                 }
               }
             }
