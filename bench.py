@@ -513,7 +513,7 @@ def main():
             pass
         tf32_peak = measure_tf32_peak()
         achieved = flops_step / (t_contract * 1e-3) / 1e12 if t_contract > 0 else None
-        roof = {"bound": "tensor", "kernel": "cl_contract_kernel + cl_pair_kernel (cta_group::2) + ghost_norm_kernel (tcgen05 kind::tf32, TMA-fed)", "achieved": achieved,
+        roof = {"bound": "tensor", "kernel": "cl_contract_kernel + cl_pair_kernel (cta_group::2) + ghost2_norm_kernel (tcgen05 kind::tf32, TMA-fed)", "achieved": achieved,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": (achieved / tf32_peak) if achieved else None,
                 "peak_source": "TF32 torch.matmul 8192^3 best of 12, measured live (MEASURED_PEAKS.json has no TF32 figure)",
                 "bf16_peak_measured": peaks.get("bf16_tflops"),
@@ -523,7 +523,7 @@ def main():
                 "whole_dp_frac": flops_step / (t_dp * 1e-3) / 1e12 / tf32_peak,
                 # dram__bytes_read+write summed over the contraction launches of one step, from the ncu --set full
                 # capture in profiles/r1_ncu_full_contraction_kernels_final.txt (B=512/GPU CelebA workload only)
-                "traffic": 2.59e9 if (wl == "celeba_d64_gc" and B == 512) else None,
+                "traffic": 2.57e9 if (wl == "celeba_d64_gc" and B == 512) else None,
                 "traffic_note": "per step (8 contraction launches, profiles/r1_ncu_full_contraction_kernels_final.txt); algorithmic operand bytes per step = "
                                 f"{2 * B * (1032196 if wl == 'celeba_d64_gc' else 4756)}"}
         line = {
