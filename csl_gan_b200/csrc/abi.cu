@@ -540,7 +540,7 @@ int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long
                 int Wo, float scale, float* dst, long long rows_total, int slot0, float* bias_rows, float* sumsq,
                 cg_stream_t stream) {
   if (B <= 0 || M <= 0) return 0;
-  if (B > 65535) return fail("batch too large for the staging grid");
+
   DevInfo d;
   if (dev_info(&d)) return 1;
   const int Q = Ho * Wo;
@@ -553,7 +553,7 @@ int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long
   if (qchunks < 1) qchunks = 1;
   if (qchunks > Q) qchunks = Q;
   int qpb = (Q + qchunks - 1) / qchunks;
-  dim3 grid((Q + qpb - 1) / qpb, B);
+  dim3 grid(B, (Q + qpb - 1) / qpb);             // batch on grid.x (no 65535 limit), position chunks on grid.y
   const bool vec4 = sm == 1 && (M % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
                     (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   if (vec4) {
@@ -587,7 +587,8 @@ int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long
   if (dev_info(&d)) return 1;
   const int n_planes = plan->n_rh * plan->n_rw;
   const int n_cb = plan->Cp / 32;
-  if (B > 65535 || n_planes * n_cb > 65535) return fail("problem too large for the staging grid");
+  if ((B + cg::kYtSamples - 1) / cg::kYtSamples > 65535 || n_planes * n_cb > 65535)
+    return fail("problem too large for the staging grid");
   cg::YtParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;

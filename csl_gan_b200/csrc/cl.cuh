@@ -331,13 +331,13 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
 // ------------------------------------------------------------------------------------------
 // Xt[m/32][(slot0+n)*Q + q][m%32] = tf32(scale * G[n][m][oh][ow]).  Optional per-sample column sums (bias
 // gradients) and per-sample sum of squares (closed-form Linear norms).
-// grid (ceil(Q/qpb), B), block = channels rounded up to a warp (<= 256); every warp writes whole 128-byte
+// grid (B, ceil(Q/qpb)), block = channels rounded up to a warp (<= 256); every warp writes whole 128-byte
 // chunk rows; a block walks `qpb` positions so the bias sums stay in registers.
 __global__ void stage_xt_kernel(const float* __restrict__ src, long long sn, long long sm, long long sh, long long sw,
                                 int M, int Wo, int Q, float scale, float* __restrict__ dst, long long rows_total,
                                 int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq, int qpb) {
-  const int n = blockIdx.y;
-  const int q_lo = blockIdx.x * qpb, q_hi = min(q_lo + qpb, Q);
+  const int n = blockIdx.x;                       // batch on grid.x: no 65535 limit
+  const int q_lo = blockIdx.y * qpb, q_hi = min(q_lo + qpb, Q);
   const float* s = src + static_cast<long long>(n) * sn;
   const int Mp = (M + 31) & ~31;
   float ssq = 0.f;
@@ -370,8 +370,8 @@ __global__ void stage_xt_kernel(const float* __restrict__ src, long long sn, lon
 __global__ void stage_xt_vec4_kernel(const float* __restrict__ src, long long sn, long long sh, long long sw, int M,
                                      int Wo, int Q, float scale, float* __restrict__ dst, long long rows_total,
                                      int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq, int qpb) {
-  const int n = blockIdx.y;
-  const int q_lo = blockIdx.x * qpb, q_hi = min(q_lo + qpb, Q);
+  const int n = blockIdx.x;                       // batch on grid.x: no 65535 limit
+  const int q_lo = blockIdx.y * qpb, q_hi = min(q_lo + qpb, Q);
   const int mv = M >> 2;                         // channel vectors
   const int lanes_q = blockDim.x / mv;           // positions handled in parallel (>= 1)
   const int tq = threadIdx.x / mv, tm = threadIdx.x - tq * mv;
@@ -408,8 +408,8 @@ __global__ void stage_xt_vec4_kernel(const float* __restrict__ src, long long sn
 __global__ void stage_xt_vec4_wide_kernel(const float* __restrict__ src, long long sn, long long sh, long long sw, int M,
                                           int Wo, int Q, float scale, float* __restrict__ dst, long long rows_total,
                                           int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq, int qpb) {
-  const int n = blockIdx.y;
-  const int q_lo = blockIdx.x * qpb, q_hi = min(q_lo + qpb, Q);
+  const int n = blockIdx.x;                       // batch on grid.x: no 65535 limit
+  const int q_lo = blockIdx.y * qpb, q_hi = min(q_lo + qpb, Q);
   const int mv = M >> 2;
   float ssq = 0.f;
   for (int tm = threadIdx.x; tm < mv; tm += blockDim.x) {
