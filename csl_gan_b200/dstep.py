@@ -167,20 +167,24 @@ class DiscriminatorStep:
                 eng.enable_hooks()
         if use_is:
             img = img.detach().requires_grad_(True)
-        if use_gc and opt.grad_clip_mode[:8] == "adaptive":
-            self.update_adaptive_clipping_params(fake_img, fake_y)
+        try:
+            if use_gc and opt.grad_clip_mode[:8] == "adaptive":
+                self.update_adaptive_clipping_params(fake_img, fake_y)
 
-        d_fake, d_fake_loss, d_fake_aux_loss = self._fake_loss(fake_img, fake_y)
-        d_real, d_real_aux, d_real_loss, d_real_aux_loss = self._real_loss(img, labels)
-        d_loss = d_real_loss + d_fake_loss + d_real_aux_loss + d_fake_aux_loss
-        res = DStepResult(d_real_loss.detach(), d_fake_loss.detach(), d_real.detach(), d_fake.detach())
-        if opt.use_aux_loss:
-            res.d_real_aux_loss, res.d_real_aux = d_real_aux_loss.detach(), d_real_aux.detach()
+            d_fake, d_fake_loss, d_fake_aux_loss = self._fake_loss(fake_img, fake_y)
+            d_real, d_real_aux, d_real_loss, d_real_aux_loss = self._real_loss(img, labels)
+            d_loss = d_real_loss + d_fake_loss + d_real_aux_loss + d_fake_aux_loss
+            res = DStepResult(d_real_loss.detach(), d_fake_loss.detach(), d_real.detach(), d_fake.detach())
+            if opt.use_aux_loss:
+                res.d_real_aux_loss, res.d_real_aux = d_real_aux_loss.detach(), d_real_aux.detach()
 
-        if opt.per_sample_grad and use_dp:
-            # grad_outputs of every captured layer, without the (unused) batch-summed weight gradients
-            eng.backward(d_loss) if self.skip_weight_grads else d_loss.backward()
-            eng.disable_hooks()
+            if opt.per_sample_grad and use_dp:
+                # grad_outputs of every captured layer, without the (unused) batch-summed weight gradients
+                eng.backward(d_loss) if self.skip_weight_grads else d_loss.backward()
+        finally:
+            # also on an exception: the frozen-weights mode must hand the parameters back to autograd
+            if opt.per_sample_grad and use_dp:
+                eng.disable_hooks()
         if use_gc:
             if self.collect_stats:
                 with torch.no_grad():
