@@ -570,6 +570,10 @@ int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long
     else
       cg::stage_xt_vec4_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
                                                                       slot0, bias_rows, sumsq, qpb);
+  } else if (sm == 1 && (M % 2) == 0 && (sn % 2) == 0 && (sh % 2) == 0 && (sw % 2) == 0 &&
+             (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+    cg::stage_xt_vec2_kernel<<<grid, 256, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
+                                                          bias_rows, sumsq, qpb);
   } else {
     cg::stage_xt_kernel<<<grid, block, 0, S(stream)>>>(src, sn, sm, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
                                                        bias_rows, sumsq, qpb);

@@ -438,6 +438,43 @@ __global__ void stage_xt_vec4_wide_kernel(const float* __restrict__ src, long lo
   }
 }
 
+// float2 variant for channels-fastest rows that are a multiple of 2 but not of 4 floats (the 794-wide
+// conditional MNIST input): block-sized strips of channel pairs, 8-byte loads and stores.
+__global__ void stage_xt_vec2_kernel(const float* __restrict__ src, long long sn, long long sh, long long sw, int M,
+                                     int Wo, int Q, float scale, float* __restrict__ dst, long long rows_total,
+                                     int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq, int qpb) {
+  const int n = blockIdx.x;
+  const int q_lo = blockIdx.y * qpb, q_hi = min(q_lo + qpb, Q);
+  const int mv = M >> 1;
+  float ssq = 0.f;
+  for (int tm = threadIdx.x; tm < mv; tm += blockDim.x) {
+    const int m = 2 * tm;
+    const float* s = src + static_cast<long long>(n) * sn + m;
+    float* d = dst + (static_cast<long long>(m >> 5) * rows_total + static_cast<long long>(slot0 + n) * Q) * 32 + (m & 31);
+    float2 bs = make_float2(0.f, 0.f);
+    for (int q = q_lo; q < q_hi; ++q) {
+      const int oh = q / Wo, ow = q - oh * Wo;
+      float2 v = __ldg(reinterpret_cast<const float2*>(s + oh * sh + ow * sw));
+      v.x *= scale; v.y *= scale;
+      bs.x += v.x; bs.y += v.y;
+      ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, ssq));
+      v.x = round_tf32(v.x); v.y = round_tf32(v.y);
+      *reinterpret_cast<float2*>(d + static_cast<long long>(q) * 32) = v;
+    }
+    if (bias_rows) {
+      float* b = bias_rows + static_cast<long long>(slot0 + n) * M + m;
+      atomicAdd(b, bs.x); atomicAdd(b + 1, bs.y);
+    }
+  }
+  // the chunk-row tail [M, round_up(M, 32)) must read as zero for the contraction: written once at allocation
+  // (torch.zeros) and never touched by any staging kernel
+  if (sumsq) {
+    __shared__ float sh_red[32];
+    ssq = block_sum(ssq, sh_red);
+    if (threadIdx.x == 0) atomicAdd(sumsq + slot0 + n, ssq);
+  }
+}
+
 struct YtParams {
   int B, C, H, W;              // source [B][C][H][W] through strides
   long long sn, sc, sh_, sw_;
