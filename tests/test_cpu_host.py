@@ -218,3 +218,22 @@ def test_split_k_group_count_keeps_the_last_wave_full():
         eff_old = items_old / (-(-items_old // ctas) * ctas)
         assert eff >= eff_old - 0.004 * 64, (n_tiles, units, ctas, g, eff, eff_old)
     assert _pick_split_k(100, 512, 148) >= 4                     # the 4x4 layer of the CelebA critic: 1.35 waves before
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm of the bench contract): ONE JSON line on stdout, whatever libraries
+    print; the keys the driver reads are present.  MNIST workload so the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "mnist_gc",
+                           "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, proc.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "mnist_gc" and d["gpu_launches"] == 0
