@@ -183,6 +183,11 @@ typedef struct cg_ghost_desc {
   int max_ctas;
 } cg_ghost_desc;
 
+/* Two kernels behind one entry point.  When a stride-residue plane has at most 128 positions (Hs*Ws <= 128: the
+ * 8x8 and 4x4 layers of the CelebA critics) the activation Gram is built ONCE PER PLANE,
+ *     UU[q,q'] = sum_taps P_plane(tap)[a_tap(q), a_tap(q')],   P_pl = Y_pl Y_pl^T,
+ * and the taps are a gather-sum in the epilogue (csrc/ghost2.cuh); otherwise one Gram k-block per tap and chunk
+ * (csrc/ghost.cuh).  Environment CSLGAN_GHOST_V1=1 forces the latter (A/B measurements). */
 int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
