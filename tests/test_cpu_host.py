@@ -237,3 +237,24 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == "mnist_gc" and d["gpu_launches"] == 0
+
+
+def test_layer_geometry_matches_torch_output_shapes():
+    """ClLayerPlan.geometry (host logic): window grids of Conv2d and the swapped roles of ConvTranspose2d."""
+    import torch
+    from torch import nn
+    from csl_gan_b200.cl_plan import ClLayerPlan
+    for conv, x in ((nn.Conv2d(3, 8, 5, stride=2, padding=2), torch.zeros(2, 3, 64, 64)),
+                    (nn.Conv2d(4, 6, 3, stride=1, padding=0, dilation=2), torch.zeros(2, 4, 13, 12)),
+                    (nn.Conv2d(5, 7, (3, 5), stride=(1, 2), padding=(1, 2)), torch.zeros(1, 5, 9, 11))):
+        y = conv(x)
+        Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M = ClLayerPlan.geometry(conv, "conv", x.shape)
+        assert (Cn, H, W, M) == (x.shape[1], x.shape[2], x.shape[3], conv.out_channels)
+        assert (Ho, Wo) == tuple(y.shape[2:]) and (kh, kw) == tuple(conv.kernel_size)
+    for ct, x in ((nn.ConvTranspose2d(6, 4, 4, stride=2, padding=1), torch.zeros(2, 6, 8, 8)),
+                  (nn.ConvTranspose2d(3, 5, 3, stride=2, padding=0, output_padding=1), torch.zeros(1, 3, 5, 7))):
+        y = ct(x)
+        # the per-sample gradient of a transposed conv is the conv contraction with the roles swapped: the
+        # "unfolded" operand is the layer OUTPUT's gradient [out_channels, H, W], the plain operand the input
+        Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M = ClLayerPlan.geometry(ct, "convT", x.shape)
+        assert (Cn, H, W) == tuple(y.shape[1:]) and (Ho, Wo) == tuple(x.shape[2:]) and M == ct.in_channels
