@@ -74,6 +74,11 @@ class ContractDesc(C.Structure):
     ]
 
 
+class NoiseSeg(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_longlong), ("std_mult", C.c_double),
+                ("std_dev", C.c_void_p)]
+
+
 _PROTOS = {
     "cg_version": (C.c_int, []),
     "cg_last_error": (C.c_char_p, []),
@@ -107,8 +112,8 @@ _PROTOS = {
     "cg_row_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
     "cg_vec_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "cg_vec_fma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
-    "cg_clip_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                  C.c_void_p, C.c_void_p]),
+    "cg_clip_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_scale_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "cg_permute_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -122,6 +127,9 @@ _PROTOS = {
                                           C.c_double, C.c_ulonglong, C.c_void_p, C.c_ulonglong,
                                           C.POINTER(C.c_ulonglong), C.c_void_p]),
     "cg_philox_advance": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    "cg_noise_finalize_multi": (C.c_int, [C.POINTER(NoiseSeg), C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_void_p,
+                                          C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.POINTER(C.c_ulonglong),
+                                          C.c_void_p]),
     "cg_row_l2_norm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_row_l2_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_vec_max": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
@@ -190,6 +198,22 @@ def call(name: str, *args):
         raise CslGanCudaError(f"{name}: {lib.cg_last_error().decode(errors='replace')}")
     if launching:
         launch_count += 1
+
+
+def noise_multi(segs, in_div, in_div_dev, noise_div, noise_div_dev, seed, offset, offset_dev, stream) -> int:
+    """One launch of cg_noise_finalize_multi over `segs` = [(in tensor or None, grad tensor, std_mult, std_dev
+    tensor or None)]; returns the generator-offset advance."""
+    arr = (NoiseSeg * len(segs))()
+    for i, (tin, tg, mult, sdev) in enumerate(segs):
+        arr[i].inp = ptr(tin)
+        arr[i].grad = ptr(tg)
+        arr[i].n = tg.numel()
+        arr[i].std_mult = float(mult)
+        arr[i].std_dev = ptr(sdev)
+    inc = C.c_ulonglong(0)
+    call("cg_noise_finalize_multi", arr, len(segs), float(in_div), ptr(in_div_dev), float(noise_div), ptr(noise_div_dev),
+         int(seed), int(offset), ptr(offset_dev), C.byref(inc), stream)
+    return inc.value
 
 
 def cl_pair_ok(M: int, geom, plan) -> bool:

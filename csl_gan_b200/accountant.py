@@ -4,6 +4,12 @@ Replaces `privacy_engine.get_privacy_spent` / `opacus.privacy_analysis.compute_r
 from reference train.py:294-295, 588, mean_sampler.py:91-92 and budget_analysis.py:79-80.
 Pure CPU scalar math (Mironov, Talwar, Zhang 2019, "Renyi Differential Privacy of the Sampled
 Gaussian Mechanism"); it is not on the GPU hot path but the engine API needs it.
+
+Attribution: the log-space evaluation (`_log_add`, `_log_sub`, `_compute_log_a_int`, `_compute_log_a_frac`,
+`_compute_rdp_one`) restates, from memory and with the same private function names, the public algorithm of
+TensorFlow-Privacy's `rdp_accountant.py` as carried by pytorch/opacus 0.x `privacy_analysis.py` (Apache-2.0); the
+fork's copy is not available here.  Pinned independently by the published epsilon table of the TensorFlow-Privacy
+MNIST tutorial (tests/test_cpu_host.py::test_accountant_reproduces_the_published_tf_privacy_table).
 """
 from __future__ import annotations
 

@@ -7,6 +7,7 @@ with the repo snapshot; it is git-ignored (*.so).
 """
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -14,7 +15,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "abi.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("abi.cu", "contract.cuh", "kernels.cuh", "ptx.cuh")] + [
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
     os.path.join(os.path.dirname(HERE), "include", "cslgan_b200.h")]
 LIB = os.path.join(HERE, "libcslgan_b200.so")
 

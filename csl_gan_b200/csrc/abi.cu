@@ -801,11 +801,12 @@ int cg_vec_fma(const float* a, const float* b, float w, float* out, long long n,
   return 0;
 }
 
-int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C, int clip_lo,
-                    int clip_hi, float* factors, float* norms_out, cg_stream_t stream) {
+int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C, float c_scale,
+                    int clip_lo, int clip_hi, float* factors, float* norms_out, cg_stream_t stream) {
   if (n_slots <= 0 || n_params <= 0) return 0;
-  cg::clip_factors_kernel<<<(n_slots + 127) / 128, 128, 0, S(stream)>>>(norm2, n_params, n_slots, per_layer, C, clip_lo,
-                                                                       clip_hi, factors, norms_out);
+  if (!(c_scale > 0.f) || c_scale > 1.f) return fail("c_scale must be in (0, 1]");
+  cg::clip_factors_kernel<<<(n_slots + 127) / 128, 128, 0, S(stream)>>>(norm2, n_params, n_slots, per_layer, C, c_scale,
+                                                                       clip_lo, clip_hi, factors, norms_out);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -864,40 +865,62 @@ int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int sl
   return 0;
 }
 
-static int noise_impl(const float* in, float* grad, long long n, double in_div, double std, const float* std_dev,
-                      double noise_div, unsigned long long seed, unsigned long long offset,
-                      unsigned long long* offset_inc, cg_stream_t stream,
-                      const unsigned long long* offset_dev = nullptr) {
+int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div, const float* in_div_dev,
+                            double noise_div, const float* noise_div_dev, unsigned long long seed,
+                            unsigned long long offset, const unsigned long long* offset_dev,
+                            unsigned long long* offset_inc, cg_stream_t stream) {
   if (offset_inc) *offset_inc = 0;
-  if (n <= 0) return 0;
+  if (n_segs <= 0) return 0;
+  if (!segs) return fail("null segment table");
   DevInfo d;
   if (dev_info(&d)) return 1;
-  if (!std_dev && !(std > 0.0)) {
-    // upstream _generate_noise returns zeros when sigma*C == 0 and draws nothing from the generator
-    if (in) {
-      cg::scale_copy_kernel<<<ew_grid(n, 256, d.sm), 256, 0, S(stream)>>>(in, grad, n, recip(in_div));
-      CG_LAUNCH_CHECK();
-    } else {
-      CG_CHECK(cudaMemsetAsync(grad, 0, sizeof(float) * n, S(stream)));
-    }
-    return 0;
-  }
   if (offset % 4) return fail("philox offset must be a multiple of 4");
-  const unsigned int block = 256;
-  unsigned long long grid = (static_cast<unsigned long long>(n) + block - 1) / block;
-  const unsigned long long cap = static_cast<unsigned long long>(d.sm) * (d.max_thr / block);
-  if (grid > cap) grid = cap;
-  if (offset_inc) *offset_inc = ((static_cast<unsigned long long>(n) - 1) / (block * grid * 4) + 1) * 4;
-  cg::noise_finalize_kernel<<<static_cast<unsigned int>(grid), block, 0, S(stream)>>>(
-      in, grad, n, recip(in_div), static_cast<float>(std), recip(noise_div), seed, offset, std_dev, offset_dev);
-  CG_LAUNCH_CHECK();
+  const unsigned long long tcap = static_cast<unsigned long long>(d.sm) * (d.max_thr / 256);
+  unsigned long long off = 0;                    // advance inside this call (multiple of 4)
+  int i = 0;
+  while (i < n_segs) {
+    cg::NoiseParams p;
+    memset(&p, 0, sizeof(p));
+    long long blk = 0;
+    int m = 0;
+    for (; i < n_segs && m < cg::kNoiseMaxSegs; ++i) {
+      const cg_noise_seg& in = segs[i];
+      if (in.n <= 0) continue;
+      if (!in.grad) return fail("segment %d: null output", i);
+      cg::NoiseSeg& o = p.seg[m++];
+      o.in = in.in; o.grad = in.grad; o.n = in.n; o.std_dev = in.std_dev;
+      o.std_mult = static_cast<float>(in.std_mult);
+      // upstream _generate_noise returns zeros when sigma*C == 0 and draws nothing from the generator
+      o.draws = (in.std_dev || in.std_mult > 0.0) ? 1 : 0;
+      unsigned long long tg = (static_cast<unsigned long long>(in.n) + 255) / 256;
+      if (tg > tcap) tg = tcap;
+      o.tgrid = static_cast<unsigned int>(tg);
+      const unsigned long long trips = (static_cast<unsigned long long>(in.n) - 1) / (256 * tg * 4) + 1;
+      o.off4 = off / 4;
+      o.blk0 = blk;
+      blk += static_cast<long long>(trips * tg);
+      if (o.draws) off += trips * 4;
+    }
+    if (m == 0) break;
+    p.n_segs = m; p.n_blocks = blk;
+    p.in_mul = recip(in_div); p.noise_mul = recip(noise_div);
+    p.in_div_dev = in_div_dev; p.noise_div_dev = noise_div_dev;
+    p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
+    long long grid = blk;
+    const long long cap = static_cast<long long>(d.sm) * 8;
+    if (grid > cap) grid = cap;
+    cg::noise_multi_kernel<<<static_cast<unsigned int>(grid), 256, 0, S(stream)>>>(p);
+    CG_LAUNCH_CHECK();
+  }
+  if (offset_inc) *offset_inc = off;
   return 0;
 }
 
 int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, double std, double noise_div,
                       unsigned long long seed, unsigned long long offset, unsigned long long* offset_inc,
                       cg_stream_t stream) {
-  return noise_impl(in, grad, n, in_div, std, nullptr, noise_div, seed, offset, offset_inc, stream);
+  cg_noise_seg s = {in, grad, n, std, nullptr};
+  return cg_noise_finalize_multi(&s, 1, in_div, nullptr, noise_div, nullptr, seed, offset, nullptr, offset_inc, stream);
 }
 
 int cg_noise_finalize_graph(const float* in, float* grad, long long n, double in_div, double std_mult,
@@ -905,8 +928,9 @@ int cg_noise_finalize_graph(const float* in, float* grad, long long n, double in
                             const unsigned long long* offset_dev, unsigned long long intra_offset,
                             unsigned long long* offset_inc, cg_stream_t stream) {
   if (!offset_dev) return fail("offset_dev must not be null");
-  return noise_impl(in, grad, n, in_div, std_mult, std_dev, noise_div, seed, intra_offset, offset_inc, stream,
-                    offset_dev);
+  cg_noise_seg s = {in, grad, n, std_mult, std_dev};
+  return cg_noise_finalize_multi(&s, 1, in_div, nullptr, noise_div, nullptr, seed, intra_offset, offset_dev,
+                                 offset_inc, stream);
 }
 
 int cg_philox_advance(unsigned long long* offset_dev, unsigned long long inc, cg_stream_t stream) {
@@ -920,13 +944,27 @@ int cg_noise_finalize_dev(const float* in, float* grad, long long n, double in_d
                           const float* std_dev, double noise_div, unsigned long long seed, unsigned long long offset,
                           unsigned long long* offset_inc, cg_stream_t stream) {
   if (!std_dev) return fail("std_dev must not be null");
-  return noise_impl(in, grad, n, in_div, std_mult, std_dev, noise_div, seed, offset, offset_inc, stream);
+  cg_noise_seg s = {in, grad, n, std_mult, std_dev};
+  return cg_noise_finalize_multi(&s, 1, in_div, nullptr, noise_div, nullptr, seed, offset, nullptr, offset_inc, stream);
 }
 
 int cg_row_l2_norm(const float* src, long long rows, long long cols, float* norms, cg_stream_t stream) {
   if (rows <= 0) return 0;
   DevInfo d;
   if (dev_info(&d)) return 1;
+  if (rows < 2LL * d.sm && rows * cols >= (1LL << 18) && rows <= 65535) {
+    // few long rows: split every row over enough blocks to fill the machine (~4 blocks per SM in total)
+    long long nsplit = (4LL * d.sm + rows - 1) / rows;
+    long long per = ((cols + nsplit - 1) / nsplit + 1023) / 1024 * 1024;
+    nsplit = (cols + per - 1) / per;
+    CG_CHECK(cudaMemsetAsync(norms, 0, sizeof(float) * rows, S(stream)));
+    dim3 grid(static_cast<unsigned>(nsplit), static_cast<unsigned>(rows));
+    cg::row_sumsq_split_kernel<<<grid, 256, 0, S(stream)>>>(src, cols, cols, per, norms);
+    CG_LAUNCH_CHECK();
+    cg::sqrt_inplace_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, S(stream)>>>(norms, rows);
+    CG_LAUNCH_CHECK();
+    return 0;
+  }
   if (cols <= 256) {
     long long g = (rows + 7) / 8;
     if (g > static_cast<long long>(d.sm) * 16) g = static_cast<long long>(d.sm) * 16;
@@ -944,8 +982,15 @@ int cg_row_l2_norm_bwd(const float* g, const float* norms, const float* gout, lo
   if (rows <= 0) return 0;
   DevInfo d;
   if (dev_info(&d)) return 1;
-  long long grid = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
-  cg::row_l2_norm_bwd_kernel<<<static_cast<int>(grid), 256, 0, S(stream)>>>(g, norms, gout, rows, cols, gin);
+  // ~8 blocks per SM in total: row lanes on grid.y, column chunks of >= 1024 elements on grid.x
+  long long gy = rows < static_cast<long long>(d.sm) * 8 ? rows : static_cast<long long>(d.sm) * 8;
+  long long gx = (static_cast<long long>(d.sm) * 8 + gy - 1) / gy;
+  const long long max_gx = (cols + 1023) / 1024;
+  if (gx > max_gx) gx = max_gx;
+  if (gx < 1) gx = 1;
+  if (gy > 65535) gy = 65535;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+  cg::row_l2_norm_bwd_kernel<<<grid, 256, 0, S(stream)>>>(g, norms, gout, rows, cols, gin);
   CG_LAUNCH_CHECK();
   return 0;
 }

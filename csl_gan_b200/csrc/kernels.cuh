@@ -220,6 +220,25 @@ __global__ void row_sumsq_kernel(const float* __restrict__ src, long long rows, 
   }
 }
 
+// few long rows (the flat gradient of the immediate-sensitivity norm: rows = 1, cols = |theta|): every row is
+// split over gridDim.x blocks, partial sums meet in out[r] (zeroed by the caller) through one atomic per block;
+// sqrt_inplace_kernel finishes the norm.  grid (nsplit, rows); `per` is a multiple of 4.
+__global__ void row_sumsq_split_kernel(const float* __restrict__ src, long long cols, long long ld, long long per,
+                                       float* __restrict__ out) {
+  __shared__ float sh[32];
+  const long long r = blockIdx.y;
+  const long long lo = static_cast<long long>(blockIdx.x) * per;
+  if (lo >= cols) return;
+  const long long len = (lo + per <= cols) ? per : cols - lo;
+  const float s = block_sum(row_sumsq_device(src + r * ld + lo, len), sh);
+  if (threadIdx.x == 0) atomicAdd(out + r, s);
+}
+
+__global__ void sqrt_inplace_kernel(float* __restrict__ v, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = sqrtf(v[i]);
+}
+
 // small rows: one warp per row
 __global__ void row_sumsq_warp_kernel(const float* __restrict__ src, long long rows, long long cols, long long ld,
                                       float* __restrict__ out, int accumulate, int take_sqrt) {
@@ -298,7 +317,7 @@ __global__ void vec_fma_kernel(const float* __restrict__ a, const float* __restr
 }
 
 __global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_params, int n_slots, int per_layer,
-                                    const float* __restrict__ C, int clip_lo, int clip_hi,
+                                    const float* __restrict__ C, float c_scale, int clip_lo, int clip_hi,
                                     float* __restrict__ factors, float* __restrict__ norms_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
@@ -307,7 +326,7 @@ __global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_param
     for (int k = 0; k < n_params; ++k) {
       const float n = sqrtf(norm2[static_cast<long long>(k) * n_slots + s]);
       if (norms_out) norms_out[static_cast<long long>(k) * n_slots + s] = n;
-      const float f = fminf(C[k] / (n + 1e-6f), 1.0f);
+      const float f = fminf((c_scale == 1.0f ? C[k] : C[k] * c_scale) / (n + 1e-6f), 1.0f);
       factors[static_cast<long long>(k) * n_slots + s] = clipped ? f : 1.0f;
     }
   } else {
@@ -315,7 +334,7 @@ __global__ void clip_factors_kernel(const float* __restrict__ norm2, int n_param
     for (int k = 0; k < n_params; ++k) tot += norm2[static_cast<long long>(k) * n_slots + s];
     const float n = sqrtf(tot);
     if (norms_out) norms_out[s] = n;
-    const float f = fminf(C[0] / (n + 1e-6f), 1.0f);
+    const float f = fminf((c_scale == 1.0f ? C[0] : C[0] * c_scale) / (n + 1e-6f), 1.0f);
     factors[s] = clipped ? f : 1.0f;
   }
 }
@@ -411,40 +430,92 @@ __global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int
 }
 
 // ------------------------------------------------------------------------------------------
-// Philox noise, bit-compatible with torch's CUDA normal_ (see header comment of the ABI)
-// launched with exactly torch's geometry: block 256, grid = min(SMs*(maxThreads/256), ceil(n/256))
+// Philox noise, bit-compatible with torch's CUDA normal_ (see header comment of the ABI).
+// torch launches, per tensor, block 256 and grid = min(SMs*(maxThreads/256), ceil(n/256)); thread `idx` runs
+// curand_init(seed, idx, offset) and in loop trip k writes elements idx + nthreads*(4k + ii), ii < 4, from ONE
+// curand_normal4.  Philox4_32_10 is counter based: that draw is philox(key = seed, ctr = {offset/4 + k, idx}), so
+// the launch geometry is free.  One launch covers every tensor of the step: a block handles 256 consecutive `idx`
+// of one (tensor, k) and finds its tensor in a table of at most kNoiseMaxSegs entries.
 // ------------------------------------------------------------------------------------------
+constexpr int kNoiseMaxSegs = 24;
+
+struct NoiseSeg {
+  const float* in;
+  float* grad;
+  long long n;
+  const float* std_dev;
+  float std_mult;
+  unsigned int tgrid;                  // torch's grid for this tensor: nthreads = 256 * tgrid
+  unsigned long long off4;             // (offset of this tensor inside the launch) / 4
+  long long blk0;                      // first work block of this segment; work blocks = trips * tgrid
+  int draws;                           // 0: no noise for this segment (std == 0 on the host path)
+};
+
+struct NoiseParams {
+  NoiseSeg seg[kNoiseMaxSegs];
+  int n_segs;
+  long long n_blocks;
+  float in_mul, noise_mul;             // fp32 reciprocals (<= 0: no division)
+  const float* in_div_dev;             // device scalars overriding the two above
+  const float* noise_div_dev;
+  unsigned long long seed, offset;
+  const unsigned long long* offset_dev;
+};
+
 __global__ void __launch_bounds__(256, 4)
-noise_finalize_kernel(const float* in, float* grad, long long numel, float in_mul, float stdv, float noise_mul,
-                      unsigned long long seed, unsigned long long offset, const float* __restrict__ std_dev,
-                      const unsigned long long* __restrict__ offset_dev) {
-  if (std_dev) stdv = __fmul_rn(stdv, std_dev[0]);
-  // CUDA-graph mode: the generator offset lives in device memory (like torch's captured PhiloxCudaState);
-  // `offset` is then the intra-step displacement
-  if (offset_dev) offset += offset_dev[0];
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  curandStatePhilox4_32_10_t state;
-  curand_init(seed, idx, offset, &state);
-  const long long nthreads = static_cast<long long>(blockDim.x) * gridDim.x;
-  const long long rounded = ((numel - 1) / (nthreads * 4) + 1) * nthreads * 4;
-  for (long long li0 = idx; li0 < rounded; li0 += nthreads * 4) {
-    const float4 z = curand_normal4(&state);
-    const float zz[4] = {z.x, z.y, z.z, z.w};
+noise_multi_kernel(const __grid_constant__ NoiseParams p) {
+  float in_mul = p.in_mul, noise_mul = p.noise_mul;
+  if (p.in_div_dev) in_mul = __fdiv_rn(1.0f, p.in_div_dev[0]);
+  if (p.noise_div_dev) noise_mul = __fdiv_rn(1.0f, p.noise_div_dev[0]);
+  unsigned long long base = p.offset;
+  if (p.offset_dev) base += p.offset_dev[0];
+  const unsigned long long base4 = base >> 2;
+  const uint2 key = make_uint2(static_cast<unsigned int>(p.seed), static_cast<unsigned int>(p.seed >> 32));
+  for (long long b = blockIdx.x; b < p.n_blocks; b += gridDim.x) {
+    int s = 0;
+#pragma unroll 1
+    while (s + 1 < p.n_segs && b >= p.seg[s + 1].blk0) ++s;
+    const NoiseSeg& sg = p.seg[s];
+    const long long bl = b - sg.blk0;
+    const long long k = bl / sg.tgrid;
+    const long long idx = (bl - k * sg.tgrid) * 256 + threadIdx.x;
+    const long long nthreads = 256LL * sg.tgrid;
+    const long long li0 = idx + nthreads * 4 * k;
+    if (li0 >= sg.n) continue;
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sg.draws) {
+      float stdv = sg.std_mult;
+      if (sg.std_dev) stdv = __fmul_rn(stdv, sg.std_dev[0]);
+      const unsigned long long c = base4 + sg.off4 + static_cast<unsigned long long>(k);
+      const uint4 ctr = make_uint4(static_cast<unsigned int>(c), static_cast<unsigned int>(c >> 32),
+                                   static_cast<unsigned int>(idx), static_cast<unsigned int>(idx >> 32));
+      const uint4 r = curand_Philox4x32_10(ctr, key);
+      const float2 a = _curand_box_muller(r.x, r.y);
+      const float2 bq = _curand_box_muller(r.z, r.w);
+      zz[0] = a.x; zz[1] = a.y; zz[2] = bq.x; zz[3] = bq.y;
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        zz[ii] = __fmul_rn(zz[ii], stdv);                          // torch.normal(0, std): rand * std + 0
+        if (noise_mul > 0.f) zz[ii] = __fmul_rn(zz[ii], noise_mul);   // noise /= batch_size (torch CUDA: * 1/B)
+      }
+    }
+    float g[4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
       const long long li = li0 + nthreads * ii;
-      if (li < numel) {
-        float nz = __fmul_rn(zz[ii], stdv);                 // torch.normal(0, std): rand * std + 0
-        if (noise_mul > 0.f) nz = __fmul_rn(nz, noise_mul);  // noise /= batch_size  (torch CUDA: * 1/B)
-        float g = 0.f;
-        if (in) {
-          g = in[li];
-          if (in_mul > 0.f) g = __fmul_rn(g, in_mul);        // p.grad = summed_grad / batch_size
-          g = __fadd_rn(g, nz);                              // p.grad += noise
-        } else {
-          g = nz;
+      g[ii] = (sg.in && li < sg.n) ? sg.in[li] : 0.f;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const long long li = li0 + nthreads * ii;
+      if (li < sg.n) {
+        float v = zz[ii];
+        if (sg.in) {
+          v = g[ii];
+          if (in_mul > 0.f) v = __fmul_rn(v, in_mul);               // p.grad = summed_grad / batch_size
+          if (sg.draws) v = __fadd_rn(v, zz[ii]);                   // p.grad += noise
         }
-        grad[li] = g;
+        sg.grad[li] = v;
       }
     }
   }
@@ -454,25 +525,32 @@ __global__ void philox_advance_kernel(unsigned long long* offset_dev, unsigned l
   if (threadIdx.x == 0 && blockIdx.x == 0) offset_dev[0] += inc;
 }
 
-// no-noise variant (sigma == 0 or C == 0): grad = in / in_div
-__global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float mul) {
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = mul > 0.f ? __fmul_rn(in[i], mul) : in[i];
-}
-
 // ------------------------------------------------------------------------------------------
 // row-norm backward, vector max, fused per-sample L2 clip
 // ------------------------------------------------------------------------------------------
+// grid (column chunks, row lanes): a row is spread over gridDim.x blocks, so a single long row (rows = 1,
+// cols = |theta|) still fills the machine
 __global__ void row_l2_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norms,
                                        const float* __restrict__ gout, long long rows, long long cols,
                                        float* __restrict__ gin) {
-  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+  const bool vec = (cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gin)) & 15) == 0;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
     const float n = norms[r];
     const float s = n > 0.f ? gout[r] / n : 0.f;
     const float* gr = g + r * cols;
     float* o = gin + r * cols;
-    for (long long i = threadIdx.x; i < cols; i += blockDim.x) o[i] = gr[i] * s;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+      const long long n4 = cols >> 2;
+      for (long long i = i0; i < n4; i += stride) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(gr) + i);
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4*>(o)[i] = v;
+      }
+    } else {
+      for (long long i = i0; i < cols; i += stride) o[i] = gr[i] * s;
+    }
   }
 }
 

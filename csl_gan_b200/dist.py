@@ -37,9 +37,45 @@ def allreduce_flat(tensors: Sequence[torch.Tensor], op=None, group=None) -> List
     return out
 
 
-def global_norm_proxy(local_flat: torch.Tensor, global_flat: torch.Tensor, world: int) -> torch.Tensor:
+def global_norm_proxy(local_flat: torch.Tensor, global_flat: torch.Tensor, weight) -> torch.Tensor:
     """A scalar whose gradient w.r.t. this rank's inputs equals d||g_global||/dx_i for the samples the
-    rank holds: with v = g_global / ||g_global|| constant, d||g_global||/dx_i = <v, d g_local/dx_i> / world."""
+    rank holds: with v = g_global / ||g_global|| constant, d||g_global||/dx_i = weight * <v, d g_local/dx_i>,
+    where g_global = sum_r weight_r g_local_r.  `weight` is this rank's share of the global batch B_r / sum B
+    (a float or a 0-dim tensor; 1/world for equal shards -- an int `world` is still accepted and means that)."""
+    if isinstance(weight, int) and not isinstance(weight, bool) and weight >= 1:
+        weight = 1.0 / weight
     n = global_flat.norm(2)
     v = torch.where(n > 0, global_flat / n, torch.zeros_like(global_flat))
-    return (local_flat * v.detach()).sum() / world
+    return (local_flat * v.detach()).sum() * weight
+
+
+def allreduce_sum_and_count(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """allreduce(SUM) of a flat buffer whose LAST element carries this rank's live sample count: the clipped sums
+    and the global batch size arrive in one collective, so unequal shards (B % world != 0, a short last batch on
+    one rank) divide by the true number of samples on every rank.  In place; returns `flat`."""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def allreduce_weighted_mean(tensors: Sequence[torch.Tensor], local_count: int, group=None):
+    """Global mean gradient of per-rank MEAN gradients over shards of unequal size:
+    g = sum_r B_r g_r / sum_r B_r.  One collective (the count rides in the flat buffer).
+    Returns (list of tensors shaped like the inputs, this rank's weight B_r / sum B as a 0-dim tensor)."""
+    flat = torch.cat([t.reshape(-1) * float(local_count) for t in tensors]
+                     + [torch.full((1,), float(local_count), dtype=tensors[0].dtype, device=tensors[0].device)])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    total = flat[-1]
+    out, off = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append((flat[off:off + n] / total).view(t.shape))
+        off += n
+    return out, float(local_count) / total
+
+
+def global_batch_size(local_batch: int, device=None, group=None) -> int:
+    """Sum of the per-rank batch sizes (one tiny collective at engine construction): the sampling rate the RDP
+    accountant needs is global_batch / sample_size, not this rank's shard."""
+    t = torch.tensor([float(local_batch)], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(round(t.item()))

@@ -200,11 +200,25 @@ class DiscriminatorStep:
                 pen_real, pen_labels = self.public_batch(batch_size, labels)
                 if self._nhwc and pen_real.dim() == 4:
                     pen_real = pen_real.contiguous(memory_format=torch.channels_last)
-            if use_dp and opt.per_sample_grad:
-                if not opt.penalty_use_public_data:
-                    raise NotImplementedError(
-                        "per-sample penalties on private data (-pupd False) leak memory in the reference "
-                        "(train.py:435-436) and are not reproduced; use public data / mean samples")
+            if use_dp and opt.per_sample_grad and not opt.penalty_use_public_data:
+                # train.py:434-450: the penalty touches private data, so its per-sample gradients are added to the
+                # per-sample gradients before (re-)clipping.  The slow path of the reference, kept as such: one
+                # autograd.grad per sample into the materialised p.grad_sample[0, i] (without the reference's
+                # create_graph=True, which is what leaks there, train.py:435-436)
+                eng.expose_grad_sample_attrs()
+                penalties = calc_penalty(D, opt.penalty, pen_real, pen_labels, fake_img, fake_y, device=img.device,
+                                         per_sample=True, aux_penalty=opt.aux_penalty)
+                penalty = penalties.mean(dim=0)
+                params = list(D.parameters())
+                for i in range(len(penalties)):
+                    pg = autograd.grad(penalties[i], params, retain_graph=True, allow_unused=True)
+                    with torch.no_grad():
+                        for p, g in zip(params, pg):
+                            if g is not None:
+                                p.grad_sample[0, i] += g
+                eng.clip()
+                eng.accumulate_batch()
+            elif use_dp and opt.per_sample_grad:
                 eng.accumulate_batch()
                 penalty = calc_penalty(D, opt.penalty, pen_real, pen_labels, fake_img, fake_y, device=img.device,
                                        aux_penalty=opt.aux_penalty)

@@ -35,12 +35,14 @@ class ISPrivacyEngine:
                  alphas: Sequence[float] = tuple([1 + x / 10.0 for x in range(1, 100)] + list(range(12, 64))),
                  noise_multiplier: float, per_param: bool = False,
                  scaling_vec: Optional[Sequence[float]] = None, noise_div_batch: bool = False,
-                 process_group=None, data_parallel: bool = False, **misc):
+                 process_group=None, data_parallel: bool = False, global_batch_size: Optional[int] = None, **misc):
+        """`batch_size` is THIS rank's batch; the accountant's sampling rate uses the global batch
+        (`global_batch_size`, or the sum over ranks taken once at construction under data parallelism)."""
         L.load()
         self.module = module
         self.batch_size = batch_size
         self.sample_size = sample_size
-        self.sample_rate = batch_size / sample_size
+        self.global_batch_size = global_batch_size
         self.alphas = list(alphas)
         self.noise_multiplier = float(noise_multiplier)
         self.per_param = per_param
@@ -62,6 +64,17 @@ class ISPrivacyEngine:
         self._per_sample_sens: Optional[torch.Tensor] = None
         self._seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
         self._philox_offset = 0
+        if self.global_batch_size is None:
+            self.global_batch_size = batch_size
+            if self.data_parallel:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    from .dist import global_batch_size as _gbs
+                    self.global_batch_size = _gbs(batch_size, self.device, self.process_group)
+
+    @property
+    def sample_rate(self) -> float:
+        return self.global_batch_size / self.sample_size
 
     # ------------------------------------------------------------------ attach / seed
     def attach(self, optimizer):
@@ -105,6 +118,8 @@ class ISPrivacyEngine:
 
     def load_state_dict(self, sd: Dict):
         self.steps, self._seed, self._philox_offset = sd["steps"], sd["seed"], sd["philox_offset"]
+        if getattr(self, "_offset_dev", None) is not None:
+            self._offset_dev.fill_(self._philox_offset)      # graph-safe RNG: resume where the stream left off
         if sd.get("scaling_vec") is not None:
             self.set_scaling_vec(sd["scaling_vec"])
 
@@ -122,14 +137,14 @@ class ISPrivacyEngine:
         params = self._params
         g = autograd.grad(loss, params, create_graph=True, allow_unused=True)
         g = [gi if gi is not None else torch.zeros_like(p) for gi, p in zip(g, params)]
-        world = 1
+        weight = None                                # this rank's share of the global batch (data parallel)
         if self.data_parallel:
-            import torch.distributed as dist
-            world = dist.get_world_size(self.process_group)
             # the sensitivity is that of the GLOBAL mean gradient: every rank needs the global g before
-            # ||g|| is differentiated (two exchange steps)
-            from .dist import allreduce_flat
-            g_glob = [t / world for t in allreduce_flat([gi.detach() for gi in g], group=self.process_group)]
+            # ||g|| is differentiated (two exchange steps).  Shards may be unequal: the global mean
+            # is sum_r B_r g_r / sum_r B_r, the sample count rides in the same collective.
+            from .dist import allreduce_weighted_mean
+            g_glob, weight = allreduce_weighted_mean([gi.detach() for gi in g], inputs.shape[0],
+                                                     group=self.process_group)
         else:
             g_glob = [gi.detach() for gi in g]
         for p, gi in zip(params, g_glob):
@@ -148,11 +163,11 @@ class ISPrivacyEngine:
 
         def norm_of(local: torch.Tensor, glob: torch.Tensor) -> torch.Tensor:
             """||g_global|| as a function of this rank's inputs: with v = g_global/||g_global|| held
-            constant, d||g_global||/dx_i = <v, d g_local / dx_i> / world."""
-            if world == 1:
+            constant, d||g_global||/dx_i = weight * <v, d g_local / dx_i>."""
+            if weight is None:
                 return row_l2_norm(local.reshape(1, -1)).sum()
             from .dist import global_norm_proxy
-            return global_norm_proxy(local.reshape(-1), glob.reshape(-1), world)
+            return global_norm_proxy(local.reshape(-1), glob.reshape(-1), weight)
 
         if self.per_param:
             rows, maxes = [], []
@@ -163,13 +178,22 @@ class ISPrivacyEngine:
             self._per_sample_sens = torch.stack(rows)
             sens = torch.cat(maxes)
         else:
-            if self.scaling_vec is None:
-                loc = torch.cat([gi.reshape(-1) for gi in g])
-                glo = torch.cat([gi.reshape(-1) for gi in g_glob])
+            sv = self.scaling_vec
+            if weight is None:
+                # ||g|| over all parameters without concatenating them: sqrt(sum_k ||g_k||^2 / v_k^2); every
+                # ||g_k|| is one multi-block CUDA row norm with its own backward / double backward
+                nk = torch.stack([row_l2_norm(gi.reshape(1, -1)).sum() / (1.0 if sv is None else sv[k])
+                                  for k, gi in enumerate(g)])
+                total = nk.pow(2).sum().sqrt() if nk.requires_grad else nk.detach().pow(2).sum().sqrt()
+                ps, sens = sens_of(total)
             else:
-                loc = torch.cat([gi.reshape(-1) / v for gi, v in zip(g, self.scaling_vec)])
-                glo = torch.cat([gi.reshape(-1) / v for gi, v in zip(g_glob, self.scaling_vec)])
-            ps, sens = sens_of(norm_of(loc, glo))
+                if sv is None:
+                    loc = torch.cat([gi.reshape(-1) for gi in g])
+                    glo = torch.cat([gi.reshape(-1) for gi in g_glob])
+                else:
+                    loc = torch.cat([gi.reshape(-1) / v for gi, v in zip(g, sv)])
+                    glo = torch.cat([gi.reshape(-1) / v for gi, v in zip(g_glob, sv)])
+                ps, sens = sens_of(norm_of(loc, glo))
             self._per_sample_sens = ps
         if self.data_parallel:
             import torch.distributed as dist
@@ -192,10 +216,9 @@ class ISPrivacyEngine:
             raise RuntimeError("step() before backward()")
         self.steps += 1
         st = L.stream_ptr(self.device)
-        inc = C.c_ulonglong(0)
-        ndiv = float(self.batch_size) if self.noise_div_batch else 0.0
+        ndiv = float(self.global_batch_size) if self.noise_div_batch else 0.0
         od = getattr(self, "_offset_dev", None)
-        intra = 0
+        segs = []
         for k, p in enumerate(self._params):
             mult = self.noise_multiplier
             if self.per_param:
@@ -204,17 +227,14 @@ class ISPrivacyEngine:
                 sdev = self._sens_dev[:1]
                 if self.scaling_vec is not None:
                     mult *= self.scaling_vec[k]
-            g = p.grad
-            if od is not None:
-                L.call("cg_noise_finalize_graph", L.ptr(g), L.ptr(g), g.numel(), 0.0, mult, L.ptr(sdev), ndiv,
-                       self._seed, L.ptr(od), intra, C.byref(inc), st)
-                intra += inc.value
-            else:
-                L.call("cg_noise_finalize_dev", L.ptr(g), L.ptr(g), g.numel(), 0.0, mult, L.ptr(sdev), ndiv,
-                       self._seed, self._philox_offset, C.byref(inc), st)
-                self._philox_offset += inc.value
-        if od is not None and intra:
-            L.call("cg_philox_advance", L.ptr(od), intra, st)
+            segs.append((p.grad, p.grad, mult, sdev))
+        # ONE launch for all parameter tensors (bit-identical to one torch.normal per tensor, in order)
+        inc = L.noise_multi(segs, 0.0, None, ndiv, None, self._seed, 0 if od is not None else self._philox_offset, od, st)
+        if od is not None:
+            if inc:
+                L.call("cg_philox_advance", L.ptr(od), inc, st)
+        else:
+            self._philox_offset += inc
 
     # ------------------------------------------------------------------ accountant
     def get_privacy_spent(self, target_delta: Optional[float] = None):

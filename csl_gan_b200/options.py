@@ -2,8 +2,9 @@
 
 Keeps the hot-path flags of reference options.py:113-206 (names, short forms, choices, defaults and
 the per-dataset default tables :11-91) and the derived fields the training step reads (:230-235,
-240-256).  Dataset / output-directory / resume plumbing is out of scope (only the D
-step is rebuilt), so `parse()` takes argv and touches no files.
+240-256).  Every flag spelling of the reference CLI (options.py:116-206) parses, so an unmodified reference command
+line is accepted; dataset / output-directory / resume / logging-cadence flags are carried but ignored
+(`IGNORED_FLAGS`; SURVEY.md §8: only the D step is rebuilt), and `parse()` takes argv and touches no files.
 
 Reference quirk kept on purpose: in `fill_defaults` a value of False counts as "unset"
 (options.py:95), so e.g. CelebA cannot switch `-ispp` off.
@@ -50,6 +51,16 @@ def build_parser() -> argparse.ArgumentParser:
     a("--weights_seed", type=int, default=42)
     a("--manual_seed", type=int, default=-1)
     a("dataset", type=str, choices=["MNIST", "CelebA"])
+    # dataset / output / resume plumbing of reference options.py:121-133: accepted so that an unmodified reference
+    # command line parses; the D step never reads them (IGNORED_FLAGS below)
+    a("-d", "--data_path", type=str, default=None)
+    a("-lp", "--label_path", type=str, default=None)
+    a("-la", "--label_attr", type=str, default=None)
+    a("--download_mnist", default=False, action="store_true")
+    a("-o", "--output_dir", type=str, default=None)
+    a("-rp", "--resume_path", type=str, default=None)
+    a("-re", "--resume_epochs", type=int, default=0)
+    a("-ka", "--keep_args", type=str, nargs="*", default=[])
     a("--model", type=str, choices=["Vanilla", "DeepConvResNet"], default=None)
     a("--im_size", type=int, default=None, choices=[64, 48, 28])
     a("-ne", "--n_epochs", type=int, default=None)
@@ -61,8 +72,10 @@ def build_parser() -> argparse.ArgumentParser:
     a("-tss", "--train_set_size", type=int, default=None)
     a("-gd", "--g_device", type=str, default="cpu")
     a("-dd", "--d_device", type=str, default="cpu")
+    a("-nw", "--num_workers", type=int, default=8)
     a("--g_latent_dim", type=int, default=None)
     a("--n_d_steps", type=int, default=None)
+    a("--train_d_until_threshold", type=float, default=1e10)
     a("-cond", "--conditional", action="store_true", default=False)
     a("--g_label_emb_mode", type=str, choices=["embed", "concat"], default=None)
     a("--d_label_emb_mode", type=str, choices=["embed", "concat"], default=None)
@@ -95,6 +108,13 @@ def build_parser() -> argparse.ArgumentParser:
     a("-cpl", "--clipping_param_per_layer", type=float, nargs="*", default=None)
     a("-as", "--adaptive_scalar", type=float, default=1.5)
     a("--adaptive_stat", choices=["mean", "max"], default="mean")
+    # trimmed-mean / smooth-sensitivity knobs (reference options.py:183-188): parsed, rejected in derive() with dp_mode
+    a("--smooth_sens_t", type=float, default=0.01)
+    a("--tm_m", type=int, default=None)
+    a("--tm_max_val", type=float, default=None)
+    a("--tm_min_val", type=float, default=None)
+    a("--tm_rho_per_epoch", type=float, default=10)
+    a("--tm_sens_compute_bs", type=float, default=None)
     a("-bpc", "--backprop_clip", type=str2bool, default=False)
     a("--bpc_back_clip_param", type=float, default=0.01)
     a("--bpc_back_clip_param_pl", type=float, nargs="*", default=None)
@@ -103,8 +123,20 @@ def build_parser() -> argparse.ArgumentParser:
     a("-bpcaas", "--bpc_auto_activation_scale", type=float, default=0.2)
     a("-bpcawgs", "--bpc_auto_weight_grad_scale", type=float, default=1e-3)
     a("--bpc_during_g_train", type=str2bool, default=True)
+    a("--save_every", type=int, default=None)
+    a("--log_every", type=int, default=None)
+    a("--sample_every", type=int, default=None)
+    a("--sample_num", type=int, default=None)
     a("-p", "--profile_training", default=False, action="store_true")
     return ap
+
+
+# flags of the reference CLI that the D step does not read (data loading, output directories, resume, logging
+# cadence, dp_mode tm/sv knobs); they parse and are carried on the namespace untouched
+IGNORED_FLAGS = ("data_path", "label_path", "label_attr", "download_mnist", "output_dir", "resume_path", "resume_epochs",
+                 "keep_args", "num_workers", "train_d_until_threshold", "smooth_sens_t", "tm_m", "tm_max_val",
+                 "tm_min_val", "tm_rho_per_epoch", "tm_sens_compute_bs", "save_every", "log_every", "sample_every",
+                 "sample_num")
 
 
 def fill_defaults(opt: Namespace, table: dict) -> None:

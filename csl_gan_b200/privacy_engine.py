@@ -21,6 +21,7 @@ Fork semantics that cannot be verified here are explicit switches (SURVEY.md §8
 """
 from __future__ import annotations
 
+import math
 import types
 from itertools import cycle
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
@@ -67,9 +68,20 @@ class GradSampleView:
     def __getitem__(self, idx):
         if isinstance(idx, int):
             return _PassView(self, idx)
-        return self.materialize()[idx]
+        # anything finer than a whole pass (reference train.py:447: `p.grad_sample[0, i] += penalty_grad`) needs the
+        # real tensor: the engine materialises every parameter's per-sample gradients once, hands out views into
+        # them, and the next clip() reads norms and sums from those tensors (the slow path, as in the reference)
+        return self._e._materialized_for_write()[self._k][idx]
+
+    def __setitem__(self, idx, value):
+        t = self._e._materialized_for_write()[self._k]
+        dst = t[idx]
+        if not (isinstance(value, torch.Tensor) and value.data_ptr() == dst.data_ptr() and value.shape == dst.shape):
+            t[idx] = value
 
     def materialize(self) -> torch.Tensor:
+        if self._e._mat is not None:
+            return self._e._mat[self._k]
         return self._e.materialize_grad_sample(self._k)
 
     def __torch_function__(self, func, types_, args=(), kwargs=None):  # pragma: no cover - convenience
@@ -170,14 +182,31 @@ class PrivacyEngine:
                  accum_passes: bool = False, num_private_passes: Optional[int] = None,
                  auto_clip_and_accum_on_step: bool = True, loss_reduction: str = "mean",
                  split_clip_fake: bool = True, max_passes: int = 2, process_group=None,
-                 data_parallel: bool = False, **misc):
+                 data_parallel: bool = False, global_batch_size: Optional[int] = None,
+                 per_layer_noise: str = "l2norm", clip_margin: float = 0.0, **misc):
+        """`batch_size` is THIS rank's batch.  Under data parallelism the accountant needs the global sampling
+        rate: pass `global_batch_size`, or leave it None and the constructor sums the per-rank batch sizes with
+        one tiny allreduce.
+        `per_layer_noise`: with per-layer thresholds C_k the L2 sensitivity of the clipped sum is ||C||_2, so
+        every parameter is noised with std sigma*||C||_2 ("l2norm", what upstream opacus >= 0.10 does and what
+        `get_privacy_spent`, which accounts for noise_multiplier = sigma, assumes); "own" noises parameter k
+        with sigma*C_k (weaker privacy than the accountant reports; kept as an explicit switch because the
+        fork's choice cannot be verified).
+        `clip_margin`: factor = min(1, C*(1 - margin)/(norm + 1e-6)).  The norms and the clipped sum come from
+        TF32-rounded tensor-core operands (relative error <= 1e-3), so a clipped per-sample gradient can
+        exceed C by that much; a margin of 2**-9 makes the bound strict.  Default 0 = the reference's formula."""
         if loss_reduction not in ("mean", "sum"):
             raise ValueError("loss_reduction must be 'mean' or 'sum'")
+        if per_layer_noise not in ("l2norm", "own"):
+            raise ValueError("per_layer_noise must be 'l2norm' or 'own'")
+        if not 0.0 <= clip_margin < 1.0:
+            raise ValueError("clip_margin must be in [0, 1)")
         L.load()                                          # fail loudly, now, if the CUDA library is absent
         self.module = module
         self.batch_size = batch_size
         self.sample_size = sample_size
-        self.sample_rate = batch_size / sample_size
+        self.per_layer_noise = per_layer_noise
+        self.clip_margin = float(clip_margin)
         self.alphas = list(alphas)
         self.noise_multiplier = float(noise_multiplier)
         self.accum_passes = accum_passes
@@ -191,6 +220,7 @@ class PrivacyEngine:
         self.misc_settings = misc
         self.steps = 0
         self.hooks_enabled = True
+        self.global_batch_size = global_batch_size
         self._frozen: list = []
         self._leaf_outputs: List[torch.Tensor] = []
         self.optimizer = None
@@ -204,6 +234,13 @@ class PrivacyEngine:
         if self.device.type != "cuda":
             raise L.CslGanCudaError(
                 f"PrivacyEngine needs the module on a CUDA device (found {self.device}); there is no CPU path")
+        if self.global_batch_size is None:
+            self.global_batch_size = batch_size
+            if self.data_parallel:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    from .dist import global_batch_size as _gbs
+                    self.global_batch_size = _gbs(batch_size, self.device, self.process_group)
         self._plans: List[LayerPlan] = []
         covered = set()
         for name, layer in module.named_modules():
@@ -232,7 +269,16 @@ class PrivacyEngine:
         self._reset_capture()
         self._accum_bs = 0
         self._clipped: Optional[List[torch.Tensor]] = None
+        self._clipped_flat: Optional[torch.Tensor] = None
+        self._summed_flat: Optional[torch.Tensor] = None
+        self._n_theta = sum(p.numel() for p in self._params)
         self._sm_count = L.device_info()[0]
+
+    @property
+    def sample_rate(self) -> float:
+        """Sampling rate of the accountant: GLOBAL batch / sample size (the per-rank shard would under-report
+        epsilon by about the world size)."""
+        return self.global_batch_size / self.sample_size
 
     # ------------------------------------------------------------------ validation / attach
     def validate(self):
@@ -415,6 +461,7 @@ class PrivacyEngine:
         self._pass_count: Dict[LayerPlan, int] = {}
         self._pass_B: Dict[int, int] = {}
         self._bp_seen = set()
+        self._mat: Optional[List[torch.Tensor]] = None     # materialised grad_sample tensors a caller has written to
         self._cur_B = self.batch_size
         self._norms_valid = False
         self._factors_valid = False
@@ -446,22 +493,29 @@ class PrivacyEngine:
         """float -> flat clipping; list -> per-layer C_k; tensors stay on the device (reference
         train.py:241 passes a list, :243 a 0-dim tensor)."""
         n = len(self._params)
+        self._factors_valid = False
         if isinstance(v, torch.Tensor):
             if v.dim() == 0:
                 self._per_layer = False
-                self._thresholds_dev = v.detach().to(self.device, torch.float32).reshape(1).clone()
-                self.max_grad_norm = v
-                self._thresholds_host = None
-                return
-            self._per_layer = True
-            t = v.detach().to(self.device, torch.float32).reshape(-1)
-            if t.numel() == 1:
-                t = t.repeat(n)
-            if t.numel() != n:
-                raise ValueError(f"expected {n} per-layer thresholds, got {t.numel()}")
-            self._thresholds_dev = t.clone()
+                t = v.detach().to(self.device, torch.float32).reshape(1).clone()
+            else:
+                self._per_layer = True
+                t = v.detach().to(self.device, torch.float32).reshape(-1)
+                if t.numel() == 1:
+                    t = t.repeat(n)
+                if t.numel() != n:
+                    raise ValueError(f"expected {n} per-layer thresholds, got {t.numel()}")
+                t = t.clone()
+            self._thresholds_dev = t
             self.max_grad_norm = v
             self._thresholds_host = None
+            self._noise_c_host = None
+            if not self._per_layer:
+                self._noise_c_dev = t.expand(n).contiguous()
+            elif self.per_layer_noise == "l2norm":
+                self._noise_c_dev = t.norm(2).reshape(1).expand(n).contiguous()
+            else:
+                self._noise_c_dev = t
             return
         if isinstance(v, (list, tuple)):
             vals = [float(x) for x in v]
@@ -471,13 +525,18 @@ class PrivacyEngine:
                 raise ValueError(f"expected {n} per-layer thresholds, got {len(vals)}")
             self._per_layer = True
             self.max_grad_norm = list(v)
+            if self.per_layer_noise == "l2norm":
+                self._noise_c_host = [math.sqrt(sum(c * c for c in vals))] * n
+            else:
+                self._noise_c_host = list(vals)
         else:
             vals = [float(v)]
             self._per_layer = False
             self.max_grad_norm = float(v)
+            self._noise_c_host = vals * n
         self._thresholds_host = vals
         self._thresholds_dev = torch.tensor(vals, dtype=torch.float32, device=self.device)
-        self._factors_valid = False
+        self._noise_c_dev = None
 
     # ------------------------------------------------------------------ norms / factors
     def _check_captured(self):
@@ -491,6 +550,17 @@ class PrivacyEngine:
             return
         n_passes = self._check_captured()
         self._norm2.zero_()
+        if self._mat is not None:
+            # a caller wrote into p.grad_sample (train.py:447): norms are row reductions over the real tensors
+            st = L.stream_ptr(self.device)
+            for k, t in enumerate(self._mat):
+                R = self._params[k].numel()
+                for ps in range(t.shape[0]):
+                    B = t.shape[1]
+                    L.call("cg_row_sumsq", L.ptr(t[ps]), B, R, R, L.ptr(self._norm2[k][ps * self.Bpad:]), 0, st)
+            self._norms_valid = True
+            self._factors_valid = False
+            return
         joint = n_passes if (self.accum_passes and n_passes > 1) else 1
         if joint > 1 and len({self._pass_B[ps] for ps in range(n_passes)}) != 1:
             raise RuntimeError("accum_passes=True needs the same batch size in every pass")
@@ -529,11 +599,12 @@ class PrivacyEngine:
         if (not self.accum_passes) and (not self.split_clip_fake) and self.num_private_passes is not None:
             clip_lo = (self._n_passes() - self.num_private_passes) * self.Bpad
         st = L.stream_ptr(self.device)
+        c_scale = 1.0 - self.clip_margin
         if self._per_layer:
-            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 1, L.ptr(self._thresholds_dev), clip_lo, clip_hi,
+            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 1, L.ptr(self._thresholds_dev), c_scale, clip_lo, clip_hi,
                    L.ptr(self._factors), L.ptr(self._norms), st)
         else:
-            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 0, L.ptr(self._thresholds_dev), clip_lo, clip_hi,
+            L.call("cg_clip_factors", L.ptr(self._norm2), n, S, 0, L.ptr(self._thresholds_dev), c_scale, clip_lo, clip_hi,
                    L.ptr(self._factors), L.ptr(self._flat_norms), st)
         # slots past the live batch of a pass (batch smaller than the padded slot count) may hold the staged
         # rows of an earlier, larger step; clip() contracts whole slot ranges, so their factor must be 0
@@ -581,6 +652,27 @@ class PrivacyEngine:
                1 if stat == "max" else 0, float(scalar), L.ptr(out), L.stream_ptr(self.device))
         return out
 
+    def _materialized_for_write(self) -> List[torch.Tensor]:
+        """Materialise every parameter's [n_passes, B, *shape] per-sample gradients (once per capture) so a caller
+        can modify them in place; norms, factors and the clipped sum are then recomputed from these tensors."""
+        if self._mat is None:
+            mats = [self.materialize_grad_sample(k).contiguous() for k in range(len(self._params))]
+            self._mat = mats
+        self._norms_valid = False
+        self._factors_valid = False
+        return self._mat
+
+    def _clip_from_materialized(self, outs: List[torch.Tensor]):
+        st = L.stream_ptr(self.device)
+        for k, t in enumerate(self._mat):
+            R = self._params[k].numel()
+            tmp = torch.empty(R, device=self.device)
+            frow = self._factors[k if self._per_layer else 0]
+            for ps in range(t.shape[0]):
+                L.call("cg_weighted_colsum", L.ptr(t[ps]), L.ptr(frow[ps * self.Bpad:]), 0, t.shape[1], R, L.ptr(tmp),
+                       1 if ps > 0 else 0, st)
+            outs[k].copy_(tmp.view(self._params[k].shape))
+
     def materialize_grad_sample(self, p_idx: int) -> torch.Tensor:
         """[n_passes, B, *p.shape] (rare path; reference train.py:447 and tests)."""
         n_passes = self._check_captured()
@@ -611,7 +703,20 @@ class PrivacyEngine:
         split mode are produced already added together; accum_grads_across_passes() is then a no-op."""
         n_passes = self._check_captured()
         self._compute_factors()
-        outs = [torch.empty_like(p) for p in self._params]
+        # ONE flat buffer [|theta| + 1]: the parameters' clipped sums are views into it (same strides as the
+        # parameter, so channels_last weights keep their layout) and the last element carries the live batch
+        # count -> the data-parallel exchange is one allreduce of this buffer, no concatenation
+        flat = torch.empty(self._n_theta + 1, device=self.device)
+        outs, off = [], 0
+        for p in self._params:
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            outs.append(flat[off:off + p.numel()].as_strided(p.shape, p.stride()) if dense else torch.empty_like(p))
+            off += p.numel()
+        self._clipped_flat = flat
+        if self._mat is not None:
+            self._clip_from_materialized(outs)
+            self._clipped = outs
+            return outs
         slot_hi = (n_passes - 1) * self.Bpad + self._pass_B[n_passes - 1]
         for plan in self._plans:
             live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
@@ -656,16 +761,40 @@ class PrivacyEngine:
         """p.summed_grad (+)= clipped sum; a SUM, not a mean (reference train.py:417, 431)."""
         if self._clipped is None:
             raise RuntimeError("accumulate_batch() called before clip()")
-        for p, c in zip(self._params, self._clipped):
-            if getattr(p, "summed_grad", None) is None:
+        fresh = all(getattr(p, "summed_grad", None) is None for p in self._params)
+        if fresh:
+            for p, c in zip(self._params, self._clipped):
                 p.summed_grad = c
-            else:
-                p.summed_grad.add_(c)
+            self._summed_flat = self._clipped_flat
+        elif self._summed_views_intact() and self._clipped_flat is not None:
+            self._summed_flat.add_(self._clipped_flat)          # gradient accumulation: one kernel, count included
+        else:
+            self._summed_flat = None
+            for p, c in zip(self._params, self._clipped):
+                if getattr(p, "summed_grad", None) is None:
+                    p.summed_grad = c
+                else:
+                    p.summed_grad.add_(c)
         # only the private pass counts towards the batch size (both passes hold the same B)
         self._accum_bs += self._cur_B
         self._clipped = None
+        self._clipped_flat = None
         self._reset_capture()
         self._drop_grad_sample_attrs()
+
+    def _summed_views_intact(self) -> bool:
+        """Are the p.summed_grad tensors still the views into `_summed_flat` this engine handed out?  (The caller
+        may add to them in place, reference train.py:431; a caller that REPLACES them gets the slow path.)"""
+        flat = self._summed_flat
+        if flat is None:
+            return False
+        off = flat.data_ptr()
+        for p in self._params:
+            sg = getattr(p, "summed_grad", None)
+            if sg is None or sg.data_ptr() != off or sg.stride() != p.stride():
+                return False
+            off += 4 * p.numel()
+        return True
 
     def _drop_grad_sample_attrs(self):
         for p in self._params:
@@ -678,11 +807,11 @@ class PrivacyEngine:
             p.grad_sample = GradSampleView(self, k)
 
     def noise_stds(self) -> List[float]:
-        th = self._thresholds_host
-        if th is None:
+        """Per-parameter noise standard deviation sigma * c_k (host thresholds only): c_k = C (flat), ||C||_2
+        (per-layer, default) or C_k (per_layer_noise="own")."""
+        if self._noise_c_host is None:
             raise RuntimeError("thresholds live on the device")
-        cs = th if self._per_layer else th * len(self._params)
-        return [self.noise_multiplier * c for c in cs]
+        return [self.noise_multiplier * c for c in self._noise_c_host]
 
     def virtual_step(self):
         self.clip()
@@ -690,8 +819,8 @@ class PrivacyEngine:
 
     def step(self):
         """Engine half of the patched optimizer.step() (reference train.py:484): p.grad = summed/B,
-        noise = N(0, (sigma*C_k)^2) drawn per parameter tensor from the Philox stream, noise /= B
-        (mean reduction), p.grad += noise."""
+        noise = N(0, (sigma*c_k)^2) drawn per parameter tensor from the Philox stream, noise /= B
+        (mean reduction), p.grad += noise.  ONE kernel launch for all parameter tensors."""
         if self.auto_clip_and_accum_on_step and self._n_passes() > 0:
             self.clip()
             self.accumulate_batch()
@@ -699,57 +828,57 @@ class PrivacyEngine:
             raise ValueError("No accumulated gradients: call clip()/accumulate_batch() before step()")
         self.steps += 1
         bs = float(self._accum_bs)
+        div_dev = None
         if self.data_parallel:
-            bs = self._allreduce_summed(bs)
-        div = bs if self.loss_reduction == "mean" else 0.0
+            div_dev = self._allreduce_summed(bs)            # device scalar: the GLOBAL number of samples
+        mean = self.loss_reduction == "mean"
         st = L.stream_ptr(self.device)
-        inc = C.c_ulonglong(0)
-        host = self._thresholds_host
         od = getattr(self, "_offset_dev", None)
-        intra = 0
+        segs = []
         for k, p in enumerate(self._params):
             s = p.summed_grad
-            g = torch.empty_like(p)
-            if od is not None:
-                if host is not None:
-                    mult, cdev = self.noise_multiplier * (host[k] if self._per_layer else host[0]), None
-                else:
-                    mult = self.noise_multiplier
-                    cdev = self._thresholds_dev[k:k + 1] if self._per_layer else self._thresholds_dev[:1]
-                L.call("cg_noise_finalize_graph", L.ptr(s), L.ptr(g), s.numel(), div, mult, L.ptr(cdev), div,
-                       self._seed, L.ptr(od), intra, C.byref(inc), st)
-                intra += inc.value
-            elif host is not None:
-                std = self.noise_multiplier * (host[k] if self._per_layer else host[0])
-                L.call("cg_noise_finalize", L.ptr(s), L.ptr(g), s.numel(), div, std, div,
-                       self._seed, self._philox_offset, C.byref(inc), st)
-                self._philox_offset += inc.value
+            if self._noise_c_host is not None:
+                segs.append((s, s, self.noise_multiplier * self._noise_c_host[k], None))
             else:
-                cdev = self._thresholds_dev[k:k + 1] if self._per_layer else self._thresholds_dev[:1]
-                L.call("cg_noise_finalize_dev", L.ptr(s), L.ptr(g), s.numel(), div, self.noise_multiplier,
-                       L.ptr(cdev), div, self._seed, self._philox_offset, C.byref(inc), st)
-                self._philox_offset += inc.value
-            p.grad = g
+                segs.append((s, s, self.noise_multiplier, self._noise_c_dev[k:k + 1]))
+        div = bs if mean else 0.0
+        inc = L.noise_multi(segs, div, div_dev if mean else None, div, div_dev if mean else None, self._seed,
+                            0 if od is not None else self._philox_offset, od, st)
+        for p in self._params:
+            p.grad = p.summed_grad                           # noised in place
             p.summed_grad = None
-        if od is not None and intra:
-            L.call("cg_philox_advance", L.ptr(od), intra, st)
+        self._summed_flat = None
+        if od is not None:
+            if inc:
+                L.call("cg_philox_advance", L.ptr(od), inc, st)
+        else:
+            self._philox_offset += inc
         self._accum_bs = 0
 
-    def _allreduce_summed(self, bs: float) -> float:
-        """Data parallel: one NCCL allreduce(SUM) of the flattened clipped sums; the batch size is
-        the global one; noise is then drawn identically on every rank from the shared Philox
-        (seed, offset), so all replicas apply the same update."""
-        import torch.distributed as dist
-        from .dist import allreduce_flat
-        red = allreduce_flat([p.summed_grad for p in self._params], group=self.process_group)
-        for p, r in zip(self._params, red):
-            p.summed_grad = r
-        return bs * dist.get_world_size(self.process_group)
+    def _allreduce_summed(self, bs: float) -> torch.Tensor:
+        """Data parallel: one NCCL allreduce(SUM) of the flat clipped-sum buffer, whose last element is this
+        rank's live sample count, so the divisor is the true global batch even with unequal shards; noise is then
+        drawn identically on every rank from the shared Philox (seed, offset), so all replicas apply the same
+        update.  Returns the device scalar holding the global count."""
+        from .dist import allreduce_sum_and_count
+        if self._summed_views_intact():
+            flat = self._summed_flat
+        else:
+            flat = torch.cat([p.summed_grad.reshape(-1) for p in self._params]
+                             + [torch.zeros(1, device=self.device)])
+            off = 0
+            for p in self._params:
+                p.summed_grad = flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+        flat[self._n_theta:].fill_(bs)
+        allreduce_sum_and_count(flat, group=self.process_group)
+        return flat[self._n_theta:]
 
     def zero_grad(self):
         """Patched optimizer.zero_grad (reference train.py:245): also drops captured state."""
         self._reset_capture()
         self._clipped = None
+        self._clipped_flat = None
         self._drop_grad_sample_attrs()
 
     # ------------------------------------------------------------------ accountant

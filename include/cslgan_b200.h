@@ -275,8 +275,10 @@ int cg_vec_fma(const float* a, const float* b, float w, float* out, long long n,
  *                   norms_out[0][s] = total
  *   per_layer != 0: factors[k][s] = min(1, C[k]/(sqrt(norm2[k][s])+1e-6)); norms_out[k][s] = sqrt(..)
  *   clip_lo..clip_hi: slots outside this range get factor 1 (unclipped non-private pass switch).
+ *   c_scale in (0, 1]: the thresholds are multiplied by it (1 = the reference's formula; 1 - 2^-9 makes
+ *   ||factor * G|| <= C strict under the TF32 rounding of the norms).
  * C is a DEVICE array (so adaptive clipping never syncs the host). */
-int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C,
+int cg_clip_factors(const float* norm2, int n_params, int n_slots, int per_layer, const float* C, float c_scale,
                     int clip_lo, int clip_hi, float* factors, float* norms_out, cg_stream_t stream);
 
 /* dst[r][slot*slot_stride + q] = tf32(src[...] * factor[slot]) for slot in [slot_lo, slot_hi). */
@@ -327,6 +329,30 @@ int cg_noise_finalize_graph(const float* in, float* grad, long long n, double in
                             const unsigned long long* offset_dev, unsigned long long intra_offset,
                             unsigned long long* offset_inc, cg_stream_t stream);
 int cg_philox_advance(unsigned long long* offset_dev, unsigned long long inc, cg_stream_t stream);
+
+/* Multi-tensor form: ONE launch noises every parameter tensor of the step (the patched optimizer.step() loops over
+ * the parameters, reference train.py:484; upstream privacy_engine.step).  Equivalent, bit for bit, to calling
+ * cg_noise_finalize / _dev / _graph on the segments in order with the generator offset advancing between them:
+ * Philox4_32_10 is counter based, so the element torch's thread `idx` would draw in its k-th loop trip is
+ * philox(seed, subsequence = idx, counter = offset/4 + k) whatever launch geometry computes it.  Blocks look the
+ * segment up in a small table (torch's grid for that tensor, its offset inside the step).
+ *   std of segment s = std_mult * (std_dev ? std_dev[0] : 1); a segment with std_dev == NULL and std_mult == 0
+ *   draws nothing and does not advance the offset (upstream _generate_noise returns zeros for sigma*C == 0).
+ *   in_div_dev / noise_div_dev: optional DEVICE scalars that override in_div / noise_div (the global batch size
+ *   that arrives with the allreduce under data parallelism); the fp32 reciprocal is taken on the device.
+ *   offset_dev: optional DEVICE generator offset (CUDA-graph replay), added to `offset`.
+ * *offset_inc receives the total advance over all segments. */
+typedef struct cg_noise_seg {
+  const float* in;           /* summed gradient; may be NULL (pure noise) or == grad           */
+  float* grad;
+  long long n;
+  double std_mult;
+  const float* std_dev;      /* device scalar or NULL                                          */
+} cg_noise_seg;
+int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div, const float* in_div_dev,
+                            double noise_div, const float* noise_div_dev, unsigned long long seed,
+                            unsigned long long offset, const unsigned long long* offset_dev,
+                            unsigned long long* offset_inc, cg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-sample row norms (reference gradient_penalty.py:52-53, 60-61; immediate sensitivity,

@@ -132,6 +132,48 @@ def test_accountant_matches_closed_forms_and_is_monotone():
     assert 2.5 < eps < 3.6
 
 
+def test_accountant_reproduces_the_published_tf_privacy_table():
+    """Independent pin of compute_rdp: the (noise multiplier, epochs) -> epsilon rows of the TensorFlow-Privacy MNIST
+    DP-SGD tutorial (n = 60000, batch 256, delta = 1e-5; its RDP accountant is the Mironov-Talwar-Zhang 2019 sampled
+    Gaussian bound with the classic conversion over the same default orders): 1.19, 3.01, 7.10."""
+    orders = [1 + x / 10.0 for x in range(1, 100)] + list(range(12, 64))
+    q = 256 / 60000
+    for sigma, epochs, eps_pub in [(1.3, 15, 1.19), (1.1, 60, 3.01), (0.7, 45, 7.10)]:
+        rdp = accountant.compute_rdp(q, sigma, epochs * 60000 // 256, orders)
+        eps, _ = accountant.get_privacy_spent(orders, rdp, 1e-5, conversion="classic")
+        assert round(eps, 2) == eps_pub, (sigma, epochs, eps)
+        eps_i, _ = accountant.get_privacy_spent(orders, rdp, 1e-5)
+        assert eps_i < eps                       # the improved (Balle et al. 2020) conversion is tighter
+
+
+def test_options_accept_every_flag_of_the_reference_cli():
+    """An unmodified reference command line parses (reference options.py:116-206 defines 109 flag spellings); the I/O,
+    resume, logging-cadence and tm/sv flags are carried on the namespace and ignored by the D step."""
+    o = options.parse(["CelebA", "-d", "/data/celeba", "-lp", "/data/list_attr.txt", "-la", "Male", "-o", "out", "-rp", "ckpt",
+                       "-re", "3", "-ka", "sigma", "d_lr", "-nw", "4", "--train_d_until_threshold", "0.5", "--download_mnist",
+                       "--smooth_sens_t", "0.02", "--tm_m", "3", "--tm_max_val", "1", "--tm_min_val", "-1",
+                       "--tm_rho_per_epoch", "5", "--tm_sens_compute_bs", "64", "--save_every", "1", "--log_every", "100",
+                       "--sample_every", "1000", "--sample_num", "16", "-p", "-dpm", "gc", "-nms", "32", "-gd", "cuda:0",
+                       "-dd", "cuda:0", "-bss", "32", "-wd", "0.0", "-wi", "10", "-eb", "8.0"])
+    assert o.data_path == "/data/celeba" and o.keep_args == ["sigma", "d_lr"] and o.log_every == 100 and o.tm_m == 3
+    assert set(options.IGNORED_FLAGS) <= set(vars(o))
+    have = {s for a in options.build_parser()._actions for s in (a.option_strings or [a.dest])}
+    ref_flags = """--weights_seed --manual_seed dataset -d --data_path -lp --label_path -la --label_attr --model --im_size
+        --download_mnist -o --output_dir -rp --resume_path -re --resume_epochs -ka --keep_args -ne --n_epochs --d_lr --g_lr
+        -wd --weight_decay -bs --batch_size -bss --batch_split_size -tss --train_set_size -gd --g_device -dd --d_device
+        -nw --num_workers --g_latent_dim --n_d_steps --train_d_until_threshold -cond --conditional --g_label_emb_mode
+        --d_label_emb_mode --conditional_arch --aux_loss_type --aux_loss_scalar --aux_penalty --d_fake_aux_loss --adam_b1
+        --adam_b2 --penalty -pss --public_set_size -nms --num_mean_samples -pupd --penalty_use_public_data -wi --warmup_iter
+        --mean_sample_size --mean_sample_noise_std --delta --sigma -eb --epsilon_budget -dpm --dp_mode -ispp
+        --imm_sens_per_param -issv --imm_sens_scaling_vec -issm --imm_sens_scaling_mode -gcs --grad_clip_split -gcm
+        --grad_clip_mode -c --clipping_param -cpl --clipping_param_per_layer -as --adaptive_scalar --adaptive_stat
+        --smooth_sens_t --tm_m --tm_max_val --tm_min_val --tm_rho_per_epoch --tm_sens_compute_bs -bpc --backprop_clip
+        --bpc_back_clip_param --bpc_back_clip_param_pl --bpc_forward_clip_param --bpc_forward_clip_param_pl -bpcaas
+        --bpc_auto_activation_scale -bpcawgs --bpc_auto_weight_grad_scale --bpc_during_g_train --save_every --log_every
+        --sample_every --sample_num -p --profile_training""".split()
+    assert len(ref_flags) == 109 and not [f for f in ref_flags if f not in have]
+
+
 def test_options_defaults_and_derived_flags():
     o = options.parse(["MNIST", "-dpm", "gc", "--conditional", "--sigma", "10"])
     assert (o.batch_size, o.clipping_param, o.sigma, o.grad_clip_mode, o.grad_clip_split) == (600, 4.0, 10.0, "standard", True)

@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from csl_gan_b200 import discriminators as DD
-from csl_gan_b200.dist import allreduce_flat, global_norm_proxy, shard_range
+from csl_gan_b200.dist import (allreduce_flat, allreduce_sum_and_count, allreduce_weighted_mean, global_batch_size,
+                               global_norm_proxy, shard_range)
 from oracle import dp_oracle as O
 
 
@@ -39,19 +40,28 @@ def _worker(rank, world, port, B, ret):
     torch.set_num_threads(1)
     D, real, fake = _data(B)
     lo, hi = shard_range(B, rank, world)
-    # ---- gc: per-rank clipped sums + ONE allreduce == full batch
+    # ---- gc: per-rank clipped sums + ONE allreduce == full batch; the live sample count rides in the same flat
+    # buffer, so unequal shards (B % world != 0) divide by the true global batch on every rank
     local = _gc_sums(copy.deepcopy(D), real[lo:hi], fake[lo:hi], hi - lo, 1.5)
-    red = allreduce_flat(local)
+    flat = torch.cat([t.reshape(-1) for t in local] + [torch.tensor([float(hi - lo)])])
+    allreduce_sum_and_count(flat)
+    assert flat[-1].item() == B and global_batch_size(hi - lo) == B
+    red, off = [], 0
+    for t in local:
+        red.append(flat[off:off + t.numel()].view(t.shape))
+        off += t.numel()
     full = _gc_sums(copy.deepcopy(D), real, fake, B, 1.5)
     gc_err = max(((a - b).norm() / b.norm()).item() for a, b in zip(red, full))
+    gc_err = max(gc_err, max(((a / flat[-1] - b / B).norm() / (b / B).norm()).item() for a, b in zip(red, full)))
     # ---- is: allreduce(mean) of g, local second-order pass through the proxy, allreduce(MAX)
     Dl = copy.deepcopy(D)
     x = real[lo:hi].clone().requires_grad_(True)
     loss = Dl.real_loss(Dl(x)[0]) + Dl.fake_loss(Dl(fake[lo:hi])[0])
     params = list(Dl.parameters())
     g = torch.autograd.grad(loss, params, create_graph=True)
-    g_glob = [t / world for t in allreduce_flat([t.detach() for t in g])]
-    proxy = global_norm_proxy(torch.cat([t.reshape(-1) for t in g]), torch.cat([t.reshape(-1) for t in g_glob]), world)
+    # per-rank losses are means over shards of unequal size: the global mean gradient is sum_r B_r g_r / sum_r B_r
+    g_glob, weight = allreduce_weighted_mean([t.detach() for t in g], hi - lo)
+    proxy = global_norm_proxy(torch.cat([t.reshape(-1) for t in g]), torch.cat([t.reshape(-1) for t in g_glob]), weight)
     sx = torch.autograd.grad(proxy, x)[0]
     s = O.row_l2_norm(sx).max().reshape(1)
     dist.all_reduce(s, op=dist.ReduceOp.MAX)
@@ -78,7 +88,7 @@ def test_two_rank_sharded_step_equals_single_process():
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 8, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 7, ret)) for r in range(2)]     # 4 + 3: unequal shards
     for p in procs:
         p.start()
     gc_err, g_err, s_err = ret.get(timeout=240)

@@ -22,7 +22,7 @@ def _step(D, real, fake, B, dev, data_parallel, seed=77, sigma=2.0, C=1.5):
     eng.clip(); eng.accum_grads_across_passes(); eng.accumulate_batch()
     opt.step()
     torch.cuda.synchronize()
-    return [p.grad.detach().cpu() for p in D.parameters()]
+    return [p.grad.detach().cpu() for p in D.parameters()], eng
 
 
 def _worker(rank, world, port, B, ret):
@@ -40,11 +40,18 @@ def _worker(rank, world, port, B, ret):
     torch.manual_seed(42)
     D = DD.MNIST_DCRN_D(n_classes=0)
     lo, hi = shard_range(B, rank, world)
-    grads = _step(D, real[lo:hi], fake[lo:hi], hi - lo, f"cuda:{rank}", True)
+    grads, eng = _step(D, real[lo:hi], fake[lo:hi], hi - lo, f"cuda:{rank}", True)
+    # the accountant sees the GLOBAL sampling rate, whatever the shard sizes
+    assert eng.global_batch_size == B and abs(eng.sample_rate - B / 60000) < 1e-12
+    # every replica holds bit-identical gradients (same allreduce result, same Philox stream)
+    flat = torch.cat([g.reshape(-1) for g in grads]).to(f"cuda:{rank}")
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    identical = all(torch.equal(both[0], b) for b in both[1:])
     if rank == 0:
-        full = _step(D, real, fake, B, "cuda:0", False)
+        full, _ = _step(D, real, fake, B, "cuda:0", False)
         err = max(((a - b).norm() / (b.norm() + 1e-12)).item() for a, b in zip(grads, full))
-        ret.put(err)
+        ret.put((err, identical))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,12 +64,13 @@ def test_two_gpu_sharded_step_matches_single_gpu():
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 16, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 15, ret)) for r in range(2)]     # 8 + 7: unequal shards
     for p in procs:
         p.start()
-    err = ret.get(timeout=500)
+    err, identical = ret.get(timeout=500)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     # the clipped sums agree to fp32 summation order; the noise term is identical on both paths
     assert err < 1e-4, err
+    assert identical

@@ -99,10 +99,10 @@ def run_oracle(D, real, fake, y, B, C, sigma=0.0):
                 captured=captured)
 
 
-def run_cuda(Dg, real, fake, y, B, C, sigma=0.0, seed=7, captures=None):
+def run_cuda(Dg, real, fake, y, B, C, sigma=0.0, seed=7, captures=None, **engine_kw):
     opt = torch.optim.Adam(Dg.parameters(), lr=0.0)
     eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=60000, noise_multiplier=sigma, max_grad_norm=C,
-                           accum_passes=False, num_private_passes=1, auto_clip_and_accum_on_step=False)
+                           accum_passes=False, num_private_passes=1, auto_clip_and_accum_on_step=False, **engine_kw)
     eng.disable_hooks()
     eng.attach(opt)
     eng._set_seed(seed)
@@ -134,6 +134,32 @@ def run_cuda(Dg, real, fake, y, B, C, sigma=0.0, seed=7, captures=None):
     torch.cuda.synchronize()
     return dict(norms=[n.clone() for n in all_norms], factors=factors, per_param_norms=per_param, summed=summed,
                 grads=grads, engine=eng)
+
+
+def run_oracle_chunked(D, real, fake, y, B, C, chunk=64):
+    """The oracle over a large batch in `chunk`-sample pieces: per-sample gradients, norms and clip factors of a
+    batch-mean loss do not depend on the other samples (B * d(mean loss)/d(out_i) = d(loss_i)/d(out_i)), so the
+    clipped sums of the chunks add up to the full-batch clipped sum while only chunk x |theta| floats are ever
+    materialised.  Captured grad_outputs are rescaled from the chunk's mean to the full batch's mean."""
+    summed, clipped, norms, pp, factors = None, None, [], [], []
+    caps = None
+    for lo_ in range(0, B, chunk):
+        hi_ = min(B, lo_ + chunk)
+        n = hi_ - lo_
+        r = run_oracle(copy.deepcopy(D), real[lo_:hi_], fake[lo_:hi_], None if y is None else y[lo_:hi_], n, C)
+        summed = r["summed"] if summed is None else [a + b for a, b in zip(summed, r["summed"])]
+        clipped = r["clipped"] if clipped is None else [a + b for a, b in zip(clipped, r["clipped"])]
+        norms.append(r["norms"]); pp.append(r["per_param_norms"]); factors.append(r["factors"])
+        if caps is None:
+            caps = [{k: ([], []) for k in layers} for layers in r["captured"]]
+        for ps, layers in enumerate(r["captured"]):
+            for k, (a, g) in layers.items():
+                caps[ps][k][0].append(a)
+                caps[ps][k][1].append(g * (n / B))
+    cat = lambda parts: [torch.cat([p[i] for p in parts], dim=1) for i in range(len(parts[0]))]
+    captured = [{k: (torch.cat(a), torch.cat(g)) for k, (a, g) in layers.items()} for layers in caps]
+    return dict(norms=cat(norms), per_param_norms=cat(pp), factors=cat(factors), summed=summed, clipped=clipped,
+                grads=[t / B for t in summed], captured=captured)
 
 
 CASES = [
@@ -183,6 +209,39 @@ def test_gc_step_matches_oracle(name, B, C):
         err = (a.cpu().double() - b.double()).norm().item()
         assert err <= REL_TOL * b.double().norm().item() + floor, (k, err, b.norm().item())
         assert rel(got["grads"][k], ref["grads"][k]) < REL_TOL or err / B <= floor / B
+
+
+CELEBA_CPL = [1000, 200, 1000, 100, 1000, 100, 1000, 5, 2500]           # reference options.py:80
+
+
+@pytest.mark.parametrize("B,C,n_clip", [
+    (128, CELEBA_CPL, 0),          # BASELINE configs 3/4: batch 128, the reference's per-layer defaults (nothing clips)
+    (128, "median-pl", 1),         # both branches of min(1, C/n) at the configured batch size
+    (512, "median-pl", 1),         # what bench.py times: 512 per GPU x 2 passes = 1024 slots, split-K over thousands of
+                                   # k-blocks, several waves of CTA pairs
+    (512, CELEBA_CPL, 0),
+])
+def test_gc_celeba_at_benchmark_batch_sizes_matches_chunked_oracle(B, C, n_clip):
+    """the CelebA configurations that are timed are compared with the oracle at the size they are
+    timed at (the oracle runs in 64-sample chunks; per-sample work is independent, the clipped sums add)."""
+    D, shape, ncls, lo = make("d64")
+    real, fake, y = batch(shape, ncls, lo, B, seed=1000 + B)
+    if isinstance(C, str):
+        probe = run_oracle_chunked(D, real, fake, y, B, 1e9)
+        C = [float(n.median()) for n in probe["per_param_norms"]]
+    ref = run_oracle_chunked(D, real, fake, y, B, C)
+    Dg = copy.deepcopy(D).to(DEV).to(memory_format=torch.channels_last)      # the layout bench.py runs the critic in
+    got = run_cuda(Dg, real, fake, y, B, C, captures=ref["captured"])
+    for k, b in enumerate(ref["per_param_norms"]):
+        np.testing.assert_allclose(got["per_param_norms"][k].cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+    for a, b in zip(got["factors"], ref["factors"]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-3, atol=1e-7)
+        assert bool((b < 0.999).any()) == bool(n_clip)
+    for k, (a, b) in enumerate(zip(got["summed"], ref["summed"])):
+        floor = 1e-5 * ref["clipped"][k].double().abs().sum(dim=0).norm().item()
+        err = (a.cpu().double() - b.double()).norm().item()
+        assert err <= REL_TOL * b.double().norm().item() + floor, (k, err, b.norm().item())
+        assert rel(got["grads"][k], ref["grads"][k]) < REL_TOL or err <= floor
 
 
 @pytest.mark.parametrize("name,B,C", [("mnist", 40, "median"), ("mnist_dcrn", 7, "median"), ("d64", 4, "median-pl"),
@@ -328,17 +387,53 @@ def test_noise_step_bit_exact_vs_torch_generator():
     eng = got["engine"]
     off = int.from_bytes(bytes(gen.get_state()[8:16].tolist()), "little")
     assert eng._philox_offset == off
-    # per-layer thresholds use sigma * C_k
-    Dg2 = copy.deepcopy(D).to(DEV)
+    # per-layer thresholds: every parameter is noised with sigma * ||C||_2, the L2 sensitivity of the per-layer
+    # clipped sum (what the accountant's noise_multiplier = sigma assumes); per_layer_noise="own" -> sigma * C_k
     Cs = [3.0, 0.2, 0.5, 0.2, 1.0, 0.5]
-    got2 = run_cuda(Dg2, real, fake, y, B, Cs, sigma=sigma, seed=seed)
-    gen.manual_seed(seed)
-    for s, g, c in zip(got2["summed"], got2["grads"], Cs):
-        noise = torch.normal(0.0, sigma * c, s.shape, device=DEV, generator=gen)
-        ref = s / B
-        noise /= B
-        ref += noise
-        assert torch.equal(g, ref)
+    c_l2 = float(np.sqrt(np.sum(np.square(np.array(Cs, dtype=np.float64)))))
+    for mode, stds in (("l2norm", [sigma * c_l2] * len(Cs)), ("own", [sigma * c for c in Cs])):
+        Dg2 = copy.deepcopy(D).to(DEV)
+        got2 = run_cuda(Dg2, real, fake, y, B, Cs, sigma=sigma, seed=seed, per_layer_noise=mode)
+        assert got2["engine"].noise_stds() == pytest.approx(stds, rel=1e-12)
+        gen.manual_seed(seed)
+        for s, g, sd in zip(got2["summed"], got2["grads"], stds):
+            noise = torch.normal(0.0, sd, s.shape, device=DEV, generator=gen)
+            ref = s / B
+            noise /= B
+            ref += noise
+            assert torch.equal(g, ref)
+    # the oracle states the same rule
+    oe = O.OracleGCEngine(copy.deepcopy(D), batch_size=B, noise_multiplier=sigma, max_grad_norm=Cs)
+    assert oe.noise_stds() == pytest.approx([sigma * c_l2] * len(Cs), rel=1e-12)
+    oe.remove()
+
+
+def test_per_layer_noise_variance_is_sigma_times_l2_norm_of_thresholds():
+    """per-layer clipping at C_k has L2 sensitivity ||C||_2; the empirical noise variance of every
+    parameter must be (sigma * ||C||_2 / B)^2, also when the thresholds live on the device (adaptive clipping)."""
+    D, shape, ncls, lo = make("mnist")
+    B, sigma = 32, 2.0
+    Cs = [3.0, 0.2, 0.5, 0.2, 1.0, 0.5]
+    c_l2 = float(np.sqrt(np.sum(np.square(Cs))))
+    real, fake, y = batch(shape, ncls, lo, B, seed=2)
+    for dev_thresholds in (False, True):
+        Dg = copy.deepcopy(D).to(DEV)
+        opt = torch.optim.SGD(Dg.parameters(), lr=0.0)
+        eng = cg.PrivacyEngine(Dg, batch_size=B, sample_size=60000, noise_multiplier=sigma,
+                               max_grad_norm=torch.tensor(Cs, device=DEV) if dev_thresholds else Cs,
+                               num_private_passes=1, auto_clip_and_accum_on_step=False)
+        eng.attach(opt)
+        eng._set_seed(11)
+        d_loss(Dg, real.to(DEV), fake.to(DEV), y.to(DEV)).backward()
+        eng.disable_hooks()
+        eng.clip(); eng.accum_grads_across_passes(); eng.accumulate_batch()
+        clean = [p.summed_grad.clone() / B for p in Dg.parameters()]
+        opt.step()
+        w = next(iter(Dg.parameters()))                       # lin1.weight: 101 632 elements
+        z = (w.grad - clean[0]).flatten().double()
+        want = sigma * c_l2 / B
+        assert abs(z.std().item() / want - 1.0) < 0.02, (z.std().item(), want)
+        assert abs(z.mean().item()) < 0.02 * want
 
 
 def test_split_clip_fake_switch_and_penalty_on_summed_grad():

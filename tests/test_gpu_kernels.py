@@ -294,13 +294,13 @@ def test_clip_factors_flat_and_per_layer():
     fac = torch.empty(n_params, S, device=DEV)
     nout = torch.empty(n_params, S, device=DEV)
     Cs = torch.tensor([2.0, 3.0, 0.5, 10.0], device=DEV)
-    L.call("cg_clip_factors", norm2.data_ptr(), n_params, S, 1, Cs.data_ptr(), 0, S, fac.data_ptr(), nout.data_ptr(), st())
+    L.call("cg_clip_factors", norm2.data_ptr(), n_params, S, 1, Cs.data_ptr(), 1.0, 0, S, fac.data_ptr(), nout.data_ptr(), st())
     norms = [norm2[k].sqrt().cpu().view(1, S) for k in range(n_params)]
     ref = O.calc_clipping_factors(norms, [2.0, 3.0, 0.5, 10.0], n_params)
     for k in range(n_params):
         np.testing.assert_allclose(fac[k].cpu().numpy(), ref[k][0].numpy(), rtol=1e-6)
         np.testing.assert_allclose(nout[k].cpu().numpy(), norms[k][0].numpy(), rtol=1e-6)
-    L.call("cg_clip_factors", norm2.data_ptr(), n_params, S, 0, Cs.data_ptr(), 10, S, fac.data_ptr(), nout.data_ptr(), st())
+    L.call("cg_clip_factors", norm2.data_ptr(), n_params, S, 0, Cs.data_ptr(), 1.0, 10, S, fac.data_ptr(), nout.data_ptr(), st())
     flat = torch.stack([n[0] for n in norms]).norm(2, dim=0)
     ref = (2.0 / (flat + 1e-6)).clamp(max=1.0)
     ref[:10] = 1.0
