@@ -502,9 +502,11 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
     eng.attach(opt_d)
     eng._set_seed(1234)
     out = {"clipping": "per-layer" if isinstance(cfg["C"], list) else "flat", "sigma": cfg["sigma"],
-           "operand_dtype": getattr(cg, "OPERAND_DTYPE", "tf32"),
-           "arithmetic": getattr(cg, "ARITHMETIC", "TF32 tensor-core operands (round-to-nearest staged), fp32 "
-                                                   "accumulation and fp32 everywhere else")}
+           "operand_dtype": eng.operand_dtype,
+           "arithmetic": ("FP16 tensor-core operands (10-bit mantissa like TF32; exact per-sample power-of-two scale, "
+                          "round-to-nearest staged), fp32 accumulation in TMEM and fp32 everywhere else"
+                          if eng.operand_dtype == "f16" else
+                          "TF32 tensor-core operands (round-to-nearest staged), fp32 accumulation and fp32 everywhere else")}
 
     # ---- value: DP machinery with captured tensors resident in HBM ---------------------------------
     caps, batch_grads = grab_captures(D, real_h.to(dev), fake_h.to(dev), y_dev)

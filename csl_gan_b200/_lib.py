@@ -39,7 +39,7 @@ class GhostPlan(C.Structure):
                 ("aw_min", C.c_int), ("Cp", C.c_int), ("rho_h", C.c_int * CG_MAX_KH), ("rho_w", C.c_int * CG_MAX_KH),
                 ("tap_plane", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("tap_hoff", C.c_int * (CG_MAX_KH * CG_MAX_KH)),
                 ("tap_woff", C.c_int * (CG_MAX_KH * CG_MAX_KH)), ("slot_stride", C.c_longlong),
-                ("merged", C.c_int), ("Cs", C.c_int), ("n_taps", C.c_int)]
+                ("merged", C.c_int), ("Cs", C.c_int), ("n_taps", C.c_int), ("cw", C.c_int)]
 
 
 ClPlan = GhostPlan
@@ -50,13 +50,15 @@ class ClDesc(C.Structure):
                 ("Yt", C.c_void_p), ("n_slots_total", C.c_int),
                 ("group_mode", C.c_int), ("n_groups", C.c_int), ("slot_lo", C.c_int), ("slot_hi", C.c_int),
                 ("epi", C.c_int), ("out", C.c_void_p), ("out_group_stride", C.c_longlong), ("max_ctas", C.c_int),
-                ("n_seg", C.c_int), ("seg_stride", C.c_int), ("pair", C.c_int)]
+                ("n_seg", C.c_int), ("seg_stride", C.c_int), ("pair", C.c_int),
+                ("half", C.c_int), ("inv_x", C.c_void_p), ("inv_y", C.c_void_p), ("out_scale", C.c_void_p)]
 
 
 class GhostDesc(C.Structure):
     _fields_ = [("Xt", C.c_void_p), ("xt_pitch", C.c_longlong), ("xt_rows", C.c_longlong),
                 ("Yt", C.c_void_p), ("n_slots_total", C.c_int), ("O", C.c_int),
-                ("slot0", C.c_int), ("n_slots", C.c_int), ("norm2", C.c_void_p), ("max_ctas", C.c_int)]
+                ("slot0", C.c_int), ("n_slots", C.c_int), ("norm2", C.c_void_p), ("max_ctas", C.c_int),
+                ("half", C.c_int), ("inv_x", C.c_void_p), ("inv_y", C.c_void_p)]
 
 
 class ContractDesc(C.Structure):
@@ -94,14 +96,27 @@ _PROTOS = {
     "cg_plan_ghost": (C.c_int, [C.POINTER(UnfoldGeom), C.POINTER(GhostPlan)]),
     "cg_ghost_norm": (C.c_int, [C.POINTER(GhostDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
     "cg_plan_cl": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int, C.POINTER(GhostPlan)]),
+    "cg_plan_cl_cw": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int, C.c_int, C.POINTER(GhostPlan)]),
     "cg_stage_xt": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
     "cg_stage_yt": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                               C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p]),
+    "cg_stage_xt_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_stage_yt_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
+                                C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_clip_mult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_scale_slots_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
+    "cg_outer_rows_cl_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_cl_contract": (C.c_int, [C.POINTER(ClDesc), C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_void_p]),
     "cg_cl_pair_ok": (C.c_int, [C.c_int, C.POINTER(UnfoldGeom), C.POINTER(GhostPlan)]),
+    "cg_cl_kblock_rows": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cg_rowpair_dot": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                  C.c_void_p]),
     "cg_joint_rows_sumsq": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -141,7 +156,7 @@ EXPORTED_SYMBOLS = tuple(_PROTOS)
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
 _NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost", "cg_plan_cl",
-              "cg_cl_pair_ok"}
+              "cg_plan_cl_cw", "cg_cl_pair_ok", "cg_cl_kblock_rows"}
 
 
 def load() -> C.CDLL:
@@ -255,10 +270,28 @@ def plan_ghost(geom: UnfoldGeom):
     return p
 
 
-def plan_cl(geom: UnfoldGeom, merged: bool) -> GhostPlan:
+def plan_cl(geom: UnfoldGeom, merged: bool, cw: int = 32) -> GhostPlan:
+    """Staging plan of the channels-last path; cw = channels per 128-byte chunk row (32 TF32 words / 64 FP16)."""
     p = GhostPlan()
-    call("cg_plan_cl", C.byref(geom), 1 if merged else 0, C.byref(p))
+    call("cg_plan_cl_cw", C.byref(geom), 1 if merged else 0, cw, C.byref(p))
     return p
+
+
+def default_operand_dtype() -> str:
+    """Operand containers of the channels-last contraction path: "f16" (default: FP16 with an exact per-sample
+    power-of-two scale; TF32's mantissa, half the bytes, twice the tensor-core rate) or "tf32"
+    (environment CSLGAN_OPERANDS overrides, for A/B measurements)."""
+    v = os.environ.get("CSLGAN_OPERANDS", "f16").lower()
+    if v not in ("f16", "tf32"):
+        raise CslGanCudaError(f"CSLGAN_OPERANDS must be f16 or tf32, got {v!r}")
+    return v
+
+
+def cl_kblock_rows(geom, half: bool):
+    """(contraction rows per k-block, slots per k-block) of the split-K clipped sum for this window grid."""
+    r, ks = C.c_int(), C.c_int()
+    call("cg_cl_kblock_rows", C.byref(geom), 1 if half else 0, C.byref(r), C.byref(ks))
+    return r.value, ks.value
 
 
 def cl_supported(Ho: int, Wo: int) -> bool:

@@ -43,9 +43,11 @@ def _channels_fastest(t: torch.Tensor) -> torch.Tensor:
 
 
 class ClLayerPlan:
-    def __init__(self, name: str, layer: nn.Module, kind: str, w_idx: int, b_idx: Optional[int], use_ghost: bool = True):
+    def __init__(self, name: str, layer: nn.Module, kind: str, w_idx: int, b_idx: Optional[int], use_ghost: bool = True,
+                 use_half: bool = True):
         self.name, self.layer, self.kind, self.w_idx, self.b_idx = name, layer, kind, w_idx, b_idx
         self.use_ghost = use_ghost
+        self.use_half = use_half
 
     # ------------------------------------------------------------------ geometry / buffers
     @staticmethod
@@ -83,15 +85,31 @@ class ClLayerPlan:
         # thin inputs (the 3-channel image) fold the filter columns into the channel axis so a 32-wide
         # channel chunk is not 90% padding; small-Q layers keep the plain layout the ghost norms need
         merged = self.kind != "linear" and Cn < MERGE_BELOW and kw > 1 and not ghost_ok
-        self.plan = L.plan_cl(self.geom, merged)
+        # FP16 operand containers (kind::f16: 16 contraction rows per instruction) wherever a per-sample k-block is a
+        # multiple of 16 rows; TF32 words otherwise (per-sample groups of 8 | Q < 16 positions)
+        # (thin inputs -- merged filter columns, e.g. 3 x 5 = 15 staged channels -- keep 32-channel TF32 chunks: a
+        # 64-channel chunk would be 77 % padding and split the 5 taps over two tiles)
+        self.half = bool(self.use_half and not merged
+                         and (self.kind == "linear" or self.Q >= 32 or self.Q % 16 == 0))
+        dt = torch.float16 if self.half else torch.float32
+        cw = self.cw = 64 if self.half else 32            # channels per 128-byte chunk row
+        self.plan = L.plan_cl(self.geom, merged, cw)
         self.n_planes = self.plan.n_rh * self.plan.n_rw
-        # chunk-major staging: Xt[m/32][slot*Q + q][32], Yt[plane*n_cb + c/32][slot][hs][ws][32]
-        self.x_chunks = _round_up(M, 32) // 32
+        self.kblock = L.cl_kblock_rows(self.geom, self.half)      # (rows, slots) per k-block of the clipped sum
+        # chunk-major staging: Xt[m/cw][slot*Q + q][cw], Yt[plane*n_cb + c/cw][slot][hs][ws][cw]
+        self.x_chunks = _round_up(M, cw) // cw
         self.x_rows = S * self.Q
-        self.Xt = torch.zeros((self.x_chunks, self.x_rows, 32), device=dev)
-        self.Xc = torch.zeros((self.x_chunks, self.x_rows, 32), device=dev)
-        self.n_cb = self.plan.Cp // 32
-        self.Yt = torch.zeros(self.n_planes * self.n_cb * S * self.plan.slot_stride, device=dev)
+        self.Xt = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
+        self.Xc = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
+        self.n_cb = self.plan.Cp // cw
+        self.Yt = torch.zeros(self.n_planes * self.n_cb * S * self.plan.slot_stride, device=dev, dtype=dt)
+        if self.half:
+            # per-slot inverse staging scales (true value = staged * inv), absmax scratch, clipped-sum multipliers
+            self.inv_x = torch.ones(S, device=dev)
+            self.inv_y = torch.ones(S, device=dev)
+            self.amax = torch.zeros(S, device=dev, dtype=torch.int32)
+            self.mult = torch.zeros(S, device=dev)
+            self.out_scale = torch.ones(2, device=dev)       # [0] = 2^E, [1] = scratch of cg_clip_mult
         self.bias_len = layer_bias_len(self.layer, self.kind)
         self.bias_rows = torch.zeros((S, self.bias_len), device=dev) if self.b_idx is not None else None
         if self.kind == "linear":
@@ -119,6 +137,11 @@ class ClLayerPlan:
     def _stage_x(self, t: torch.Tensor, slot0: int, scale: float, bias_rows, sumsq):
         t = _channels_fastest(t)
         sn, sm, sh, sw = _strides4(t)
+        if self.half:
+            L.call("cg_stage_xt_h", L.ptr(t), sn, sm, sh, sw, t.shape[0], self.M, self.Ho, self.Wo, scale,
+                   L.ptr(self.Xt), self.x_rows, slot0, L.ptr(bias_rows), L.ptr(sumsq), L.ptr(self.amax),
+                   L.ptr(self.inv_x), L.stream_ptr(t.device))
+            return
         L.call("cg_stage_xt", L.ptr(t), sn, sm, sh, sw, t.shape[0], self.M, self.Ho, self.Wo, scale,
                L.ptr(self.Xt), self.x_rows, slot0, L.ptr(bias_rows), L.ptr(sumsq), L.stream_ptr(t.device))
 
@@ -128,10 +151,18 @@ class ClLayerPlan:
         if self.kind == "linear":
             # Q = 1: Yt is [p/32][slot][p%32], the same chunked row layout as Xt; the row kernel also
             # yields ||a||^2 for the closed-form norms
-            L.call("cg_stage_xt", L.ptr(t), t.stride(0), t.stride(1), 0, 0, t.shape[0], self.Cn, 1, 1, scale,
-                   L.ptr(self.Yt), self.S, slot0, None, L.ptr(self.asq), st)
+            if self.half:
+                L.call("cg_stage_xt_h", L.ptr(t), t.stride(0), t.stride(1), 0, 0, t.shape[0], self.Cn, 1, 1, scale,
+                       L.ptr(self.Yt), self.S, slot0, None, L.ptr(self.asq), L.ptr(self.amax), L.ptr(self.inv_y), st)
+            else:
+                L.call("cg_stage_xt", L.ptr(t), t.stride(0), t.stride(1), 0, 0, t.shape[0], self.Cn, 1, 1, scale,
+                       L.ptr(self.Yt), self.S, slot0, None, L.ptr(self.asq), st)
             return
         sn, sc, sh, sw = _strides4(t)
+        if self.half:
+            L.call("cg_stage_yt_h", L.ptr(t), sn, sc, sh, sw, t.shape[0], C.byref(self.geom), C.byref(self.plan), scale,
+                   L.ptr(self.Yt), self.S, slot0, L.ptr(self.amax), L.ptr(self.inv_y), st)
+            return
         L.call("cg_stage_yt", L.ptr(t), sn, sc, sh, sw, t.shape[0], C.byref(self.geom), C.byref(self.plan), scale,
                L.ptr(self.Yt), self.S, slot0, st)
 
@@ -162,6 +193,8 @@ class ClLayerPlan:
         d.Xt, d.xt_pitch, d.xt_rows, d.M = L.ptr(X), 32, self.x_rows, self.M
         d.Yt, d.n_slots_total = L.ptr(self.Yt), self.S
         d.max_ctas = 0
+        if self.half:
+            d.half, d.inv_x, d.inv_y = 1, L.ptr(self.inv_x), L.ptr(self.inv_y)
         return d
 
     def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
@@ -194,6 +227,8 @@ class ClLayerPlan:
             gd.Yt, gd.n_slots_total, gd.O = L.ptr(self.Yt), self.S, self.M
             gd.slot0, gd.n_slots = slot0, B
             gd.norm2, gd.max_ctas = L.ptr(norm2_row[slot0:]), 0
+            if self.half:
+                gd.half, gd.inv_x, gd.inv_y = 1, L.ptr(self.inv_x), L.ptr(self.inv_y)
             L.call("cg_ghost_norm", C.byref(gd), C.byref(self.geom), C.byref(self.plan), st)
             return
         d = self._desc(self.Xt)
@@ -230,6 +265,16 @@ class ClLayerPlan:
         factor_shift != 0 reuses pass 0's (joint) factors for a later pass."""
         if self.thin:
             return                      # the clipped sum comes from the materialised per-sample gradients
+        if self.half:
+            # factor * inv_x * inv_y, brought below 1 by a common power of two that the GEMM epilogue undoes
+            if factor_shift:
+                raise L.CslGanCudaError(f"{self.name}: joint clipping needs TF32 operands")
+            st = L.stream_ptr(factor_row.device)
+            L.call("cg_clip_mult", L.ptr(factor_row), L.ptr(self.inv_x), L.ptr(self.inv_y), slot_lo, slot_hi,
+                   L.ptr(self.mult), L.ptr(self.out_scale), st)
+            L.call("cg_scale_slots_h", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * self.cw,
+                   self.Q * self.cw, slot_lo, slot_hi, L.ptr(self.mult), st)
+            return
         L.call("cg_scale_slots", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * 32, self.Q * 32,
                slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, L.stream_ptr(factor_row.device))
 
@@ -241,24 +286,28 @@ class ClLayerPlan:
         d = self._desc(self.Xc)
         # tiles per K range (mirror of cg_cl_contract) -> split K so the grid covers the machine ~2x
         n_cb, n_taps = self.n_cb, self.plan.n_taps
-        if n_cb >= 8:
-            parts = (n_cb + 7) // 8
+        maxc = 256 // self.cw                              # chunks of a 256-column tile
+        if n_cb >= maxc:
+            parts = (n_cb + maxc - 1) // maxc
             cpt = (n_cb + parts - 1) // parts
             n_nt = n_taps * ((n_cb + cpt - 1) // cpt)
         else:
-            tpt = min(8 // n_cb, n_taps)
+            tpt = min(maxc // n_cb, n_taps)
             parts = (n_taps + tpt - 1) // tpt
             tpt = (n_taps + parts - 1) // parts
             n_nt = (n_taps + tpt - 1) // tpt
         n_tiles = ((self.M + 127) // 128) * n_nt
-        units = (slot_hi - slot_lo) * max(1, self.Q // 32) if self.Q >= 32 else (slot_hi - slot_lo + 32 // self.Q - 1) // (32 // self.Q)
+        kb_rows, kb_s = self.kblock
+        units = ((slot_hi - slot_lo) * (self.Q // kb_rows) if kb_s == 1 else (slot_hi - slot_lo + kb_s - 1) // kb_s)
         if self.pair:
             # CTA pairs: 256 x 256 tiles (two half tiles of one tap x four chunks), one pair per two SMs
-            n_tiles = (self.M // 256) * ((n_taps * (n_cb // 4) + 1) // 2)
+            n_tiles = (self.M // 256) * ((n_taps * (self.plan.Cp // 128) + 1) // 2)
             n_groups = _pick_split_k(n_tiles, units, sm_count // 2)
         else:
             n_groups = _pick_split_k(n_tiles, units, sm_count)
         d.pair = 1 if self.pair else 0
+        if self.half:
+            d.out_scale = L.ptr(self.out_scale)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SPLITK, n_groups, slot_lo, slot_hi
         # where does the gradient-natural layout T[m][tap][c'] already equal the parameter's memory?
         natural = None
@@ -317,8 +366,12 @@ class ClLayerPlan:
         out = torch.zeros((B,) + tuple(w.shape), device=w.device)
         st = L.stream_ptr(w.device)
         if self.kind == "linear":
-            L.call("cg_outer_rows_cl", L.ptr(self.Xt), self.x_rows, L.ptr(self.Yt), self.S,
-                   self.M, self.Cn, slot0, B, L.ptr(out), st)
+            if self.half:
+                L.call("cg_outer_rows_cl_h", L.ptr(self.Xt), self.x_rows, L.ptr(self.Yt), self.S,
+                       self.M, self.Cn, slot0, B, L.ptr(self.inv_x), L.ptr(self.inv_y), L.ptr(out), st)
+            else:
+                L.call("cg_outer_rows_cl", L.ptr(self.Xt), self.x_rows, L.ptr(self.Yt), self.S,
+                       self.M, self.Cn, slot0, B, L.ptr(out), st)
             return out
         d = self._desc(self.Xt)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B

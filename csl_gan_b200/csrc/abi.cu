@@ -116,13 +116,14 @@ float recip(double div) { return div > 0.0 ? 1.0f / static_cast<float>(div) : 0.
 int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // generic tiled tensor map (fp32, SWIZZLE_128B); dims/strides innermost first, strides in bytes for dims 1..rank-1
-int make_tmap_nd(CUtensorMap* tm, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                 const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+int make_tmap_nd(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                 const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool half = false) {
   EncodeTiledFn enc;
   if (get_encode(&enc)) return 1;
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor base pointer must be 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, static_cast<int>(r));
@@ -145,61 +146,373 @@ void axis_plan(int K, int s, int d, int pad, int* a, int* j_of, int* rho, int* n
   }
 }
 
+// amax[slot0 + n] = max |src[n][...]| of a [B][C][H][W] tensor addressed through strides (FP16 staging scale)
+int sample_absmax(const float* src, long long sn, long long sc, long long sh, long long sw, int B, int C, int H, int W,
+                  unsigned int* amax, int slot0, int sm_count, cg_stream_t stream) {
+  CG_CHECK(cudaMemsetAsync(amax + slot0, 0, sizeof(unsigned int) * B, S(stream)));
+  const long long len = static_cast<long long>(C) * H * W;
+  long long extent = 1;
+  if (C > 1) extent += static_cast<long long>(C - 1) * sc;
+  if (H > 1) extent += static_cast<long long>(H - 1) * sh;
+  if (W > 1) extent += static_cast<long long>(W - 1) * sw;
+  if (B > 65535) return fail("batch too large for the absmax grid");
+  if (sc >= 0 && sh >= 0 && sw >= 0 && extent == len) {
+    // the sample is dense in memory (NCHW or NHWC contiguous): one linear float4 sweep, ~4 blocks per SM overall
+    long long parts = (4LL * sm_count + B - 1) / B;
+    const long long max_parts = (len + 2047) / 2048;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    dim3 grid(static_cast<unsigned>(parts), static_cast<unsigned>(B));
+    cg::absmax_dense_kernel<<<grid, 256, 0, S(stream)>>>(src, sn, len, amax, slot0);
+  } else {
+    long long parts = (len + 255) / 256;
+    if (parts > 64) parts = 64;
+    dim3 grid(static_cast<unsigned>(parts), static_cast<unsigned>(B));
+    cg::absmax_strided_kernel<<<grid, 256, 0, S(stream)>>>(src, sn, sc, sh, sw, C, H, W, amax, slot0);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Tensor maps of the channels-last operands (MN-major tiles).  rb = bytes of one 32-channel chunk row.
+//   Xt[m/32][row][m%32]: one box = kb_rows rows of four consecutive chunks -> smem [chunk][row][32]
+//   Yt[plane*n_cb + c/32][slot][hs][ws][c%32]: one box = a tap window of `cpt` consecutive chunks
+int make_cl_tmaps(CUtensorMap* tx, CUtensorMap* ty, const cg_cl_desc* d, const cg_cl_plan* plan, int n_cb, int kb_rows,
+                  int kb_w, int kb_h, int kb_s, int cpt) {
+  const bool half = d->half != 0;
+  const cuuint32_t cw = half ? 64 : 32;                    // channels per 128-byte chunk row
+  if (plan->cw != static_cast<int>(cw)) return fail("plan chunk width %d does not match the operand type", plan->cw);
+  const cuuint64_t rb = 128;
+  const CUtensorMapSwizzle sw = half ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  {
+    cuuint64_t dims[3] = {cw, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->M + cw - 1) / cw)};
+    cuuint64_t str[2] = {rb, static_cast<cuuint64_t>(d->xt_rows) * rb};
+    cuuint32_t box[3] = {cw, static_cast<cuuint32_t>(kb_rows), 128 / cw};
+    if (make_tmap_nd(tx, d->Xt, 3, dims, str, box, sw, half)) return 1;
+  }
+  {
+    const cuuint64_t slot_bytes = static_cast<cuuint64_t>(plan->slot_stride) * (half ? 2 : 4);
+    cuuint64_t dims[5] = {cw, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                          static_cast<cuuint64_t>(d->n_slots_total),
+                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * n_cb};
+    cuuint64_t str[4] = {rb, rb * plan->Ws, slot_bytes, slot_bytes * d->n_slots_total};
+    cuuint32_t box[5] = {cw, static_cast<cuuint32_t>(kb_w), static_cast<cuuint32_t>(kb_h),
+                         static_cast<cuuint32_t>(kb_s), static_cast<cuuint32_t>(cpt)};
+    if (make_tmap_nd(ty, d->Yt, 5, dims, str, box, sw, half)) return 1;
+  }
+  return 0;
+}
+
 // CTA-pair launch of the split-K clipped sum (cl_pair.cuh); `p` is the single-CTA parameter block already filled
-int launch_pair(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, const cg::ClParams& p,
-                int kb_w, int kb_h, int kb_s, cg_stream_t stream) {
-  (void)g;
+template <bool kHalf>
+int launch_pair_t(const cg_cl_desc* d, const cg_cl_plan* plan, const cg::ClParams& p, int kb_rows, int kb_w, int kb_h,
+                  int kb_s, cg_stream_t stream) {
   cg::ClPairParams q;
   memset(&q, 0, sizeof(q));
   q.M = d->M; q.n_mp = d->M / 256;
   q.C = p.C; q.n_cb = p.n_cb; q.n_taps = p.n_taps;
-  q.hpt = p.n_cb / 4; q.n_ht = p.n_taps * q.hpt; q.n_nt = (q.n_ht + 1) / 2;
+  constexpr int kHalfChunks = cg::PairCfg<kHalf>::kHalfChunks;      // chunks per 128 channels
+  q.hpt = p.n_cb / kHalfChunks; q.n_ht = p.n_taps * q.hpt; q.n_nt = (q.n_ht + 1) / 2;
   for (int t = 0; t < p.n_taps; ++t) { q.tap_plane[t] = p.tap_plane[t]; q.tap_hoff[t] = p.tap_hoff[t]; q.tap_woff[t] = p.tap_woff[t]; }
-  q.Q = p.Q; q.Wo = p.Wo; q.kb_s = p.kb_s; q.nkb_slot = p.nkb_slot;
+  q.Q = p.Q; q.Wo = p.Wo; q.kb_s = p.kb_s; q.nkb_slot = p.nkb_slot; q.kb_rows = kb_rows;
   q.oob_chunk = plan->n_rh * plan->n_rw * p.n_cb;
   q.u_lo = p.u_lo; q.u_hi = p.u_hi; q.upg = p.upg; q.n_groups = p.n_groups;
-  q.out = p.out; q.ldT = p.ldT;
+  q.out = p.out; q.ldT = p.ldT; q.out_scale = p.out_scale;
   q.n_items = static_cast<long long>(q.n_groups) * q.n_nt * q.n_mp;
   CUtensorMap tx, ty;
-  {
-    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->M + 31) / 32)};
-    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
-    cuuint32_t box[3] = {32, 32, 4};
-    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-  }
-  {
-    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
-                          static_cast<cuuint64_t>(d->n_slots_total),
-                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * p.n_cb};
-    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
-                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
-    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(kb_w), static_cast<cuuint32_t>(kb_h),
-                         static_cast<cuuint32_t>(kb_s), 4};
-    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-  }
+  if (make_cl_tmaps(&tx, &ty, d, plan, p.n_cb, kb_rows, kb_w, kb_h, kb_s, kHalfChunks)) return 1;
   DevInfo dv;
   if (dev_info(&dv)) return 1;
   static int max_pairs[64] = {0};
   int dev = 0;
   CG_CHECK(cudaGetDevice(&dev));
+  constexpr int kSmem = cg::PairCfg<kHalf>::kSmemBytes;
   if (!max_pairs[dev]) {
-    CG_CHECK(cudaFuncSetAttribute(cg::cl_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kPairSmemBytes));
+    CG_CHECK(cudaFuncSetAttribute(cg::cl_pair_kernel<kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * (dv.sm / 2)); cfg.blockDim = dim3(cg::kClThreads); cfg.dynamicSmemBytes = cg::kPairSmemBytes;
+    cfg.gridDim = dim3(2 * (dv.sm / 2)); cfg.blockDim = dim3(cg::kClThreads); cfg.dynamicSmemBytes = kSmem;
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
     cfg.attrs = &at; cfg.numAttrs = 1;
     int n = 0;
-    CG_CHECK(cudaOccupancyMaxActiveClusters(&n, cg::cl_pair_kernel, &cfg));
+    CG_CHECK(cudaOccupancyMaxActiveClusters(&n, cg::cl_pair_kernel<kHalf>, &cfg));
     if (n < 1) return fail("cl_pair_kernel: no CTA pair can be resident on this device");
     max_pairs[dev] = n;
   }
   long long pairs = max_pairs[dev];
   if (d->max_ctas > 0 && d->max_ctas / 2 < pairs) pairs = d->max_ctas / 2 > 0 ? d->max_ctas / 2 : 1;
   if (pairs > q.n_items) pairs = q.n_items;
-  cg::cl_pair_kernel<<<static_cast<int>(2 * pairs), cg::kClThreads, cg::kPairSmemBytes, S(stream)>>>(tx, ty, q);
+  cg::cl_pair_kernel<kHalf><<<static_cast<int>(2 * pairs), cg::kClThreads, kSmem, S(stream)>>>(tx, ty, q);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool kHalf>
+int launch_cl_t(const cg_cl_desc* d, const cg_cl_plan* plan, const cg::ClParams& p, int kb_rows, int kb_w, int kb_h,
+                int kb_s, int sm_count, cg_stream_t stream) {
+  CUtensorMap tx, ty;
+  if (make_cl_tmaps(&tx, &ty, d, plan, p.n_cb, kb_rows, kb_w, kb_h, kb_s, p.cpt)) return 1;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  constexpr int kSmem = cg::ClCfg<kHalf>::kSmemBytes;
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::cl_contract_kernel<kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set[dev] = true;
+  }
+  long long grid = d->max_ctas > 0 ? d->max_ctas : sm_count;
+  if (grid > p.n_items) grid = p.n_items;
+  cg::cl_contract_kernel<kHalf><<<static_cast<int>(grid), cg::kClThreads, kSmem, S(stream)>>>(tx, ty, p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+// launch `kernel` on B * parts CTAs in clusters of `parts` (1, 2, 4 or 8)
+template <typename... KArgs, typename... Args>
+int launch_clustered(void (*kernel)(KArgs...), int n_ctas, int parts, cg_stream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(n_ctas));
+  cfg.blockDim = dim3(cg::kFusedThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = S(stream);
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = static_cast<unsigned>(parts); at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  CG_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+
+// CTAs per sample of the single-pass FP16 capture (16 float4 per thread, 256 threads): 0 = sample too large
+static int fused_parts(long long floats_per_sample) {
+  const long long per = 4LL * cg::kFusedPerCta;
+  for (int parts = 1; parts <= 8; parts *= 2)
+    if (floats_per_sample <= per * parts) return parts;
+  return 0;
+}
+
+static bool fused_enabled() {
+  static const bool on = [] { const char* e = getenv("CSLGAN_FUSED_STAGE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// capture kernels of the channels-last path for either element type
+template <typename T>
+int stage_xt_t(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M, int Ho, int Wo,
+               float scale, T* dst, long long rows_total, int slot0, float* bias_rows, float* sumsq,
+               unsigned int* amax, float* inv, cg_stream_t stream) {
+  if (B <= 0 || M <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const int Q = Ho * Wo;
+  if (Q == 1 && sm == 1 && sn >= M) {
+    // Linear layers: rows [B][M]; one warp per row does the maximum, the scale, the sums and the staging
+    if (static_cast<long long>(slot0 + B) > rows_total) return fail("Xt too small for slots [%d, %d)", slot0, slot0 + B);
+    if (sizeof(T) == 2 && !inv) return fail("FP16 staging needs the inverse-scale output");
+    const long long blocks = (static_cast<long long>(B) + 7) / 8;
+    cg::stage_rows_cl_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(src, sn, B, M, scale, dst, rows_total,
+                                                                                      slot0, bias_rows, sumsq, inv);
+    CG_LAUNCH_CHECK();
+    return 0;
+  }
+  if (bias_rows) CG_CHECK(cudaMemsetAsync(bias_rows + static_cast<long long>(slot0) * M, 0, sizeof(float) * B * M, S(stream)));
+  if (sumsq) CG_CHECK(cudaMemsetAsync(sumsq + slot0, 0, sizeof(float) * B, S(stream)));
+  if (static_cast<long long>(slot0 + B) * Q > rows_total) return fail("Xt too small for slots [%d, %d)", slot0, slot0 + B);
+  if (sizeof(T) == 2) {
+    if (!amax || !inv) return fail("FP16 staging needs the amax scratch and the inverse-scale output");
+    // single pass when the sample is a dense channels-last block that a cluster of <= 8 CTAs can hold in registers
+    const int mv = M / 4;
+    const int parts = fused_parts(static_cast<long long>(Q) * M);
+    if (fused_enabled() && sm == 1 && (M % 4) == 0 && mv <= cg::kFusedThreads && (cg::kFusedThreads % mv) == 0 && sw == M &&
+        (Ho == 1 || sh == static_cast<long long>(Wo) * M) && (sn % 4) == 0 && parts > 0 && B <= (1 << 24) &&
+        (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      if (launch_clustered(cg::stage_xt_fused_kernel, B * parts, parts, stream, src, sn, M, Q, scale,
+                           reinterpret_cast<__half*>(dst), rows_total, slot0, bias_rows, inv, parts)) return 1;
+      CG_LAUNCH_CHECK();
+      return 0;
+    }
+    if (sample_absmax(src, sn, sm, sh, sw, B, M, Ho, Wo, amax, slot0, d.sm, stream)) return 1;
+  }
+  int block = ((M < 256 ? M : 256) + 31) / 32 * 32;
+  // positions per block: keep ~8 blocks per SM in flight without shredding the bias sums into atomics
+  int qchunks = static_cast<int>((8LL * d.sm + B - 1) / B);
+  if (qchunks < 1) qchunks = 1;
+  if (qchunks > Q) qchunks = Q;
+  int qpb = (Q + qchunks - 1) / qchunks;
+  dim3 grid(B, (Q + qpb - 1) / qpb);             // batch on grid.x (no 65535 limit), position chunks on grid.y
+  const bool vec4 = sm == 1 && (M % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec4) {
+    const int mv = M / 4;
+    int vblock = 256;                                         // rows wider than 1024 channels: block-sized strips
+    if (mv <= 256) {
+      vblock = mv >= 128 ? ((mv + 31) / 32 * 32) : 128;       // at least 128 threads: several positions in parallel
+      if (vblock % mv) vblock = (vblock / mv + 1) * mv;       // whole groups of channel vectors
+      if (vblock > 1024) vblock = mv;
+    }
+    if (mv > 256)
+      cg::stage_xt_vec4_wide_kernel<T><<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
+                                                                        slot0, bias_rows, sumsq, qpb, amax, inv);
+    else
+      cg::stage_xt_vec4_kernel<T><<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
+                                                                   slot0, bias_rows, sumsq, qpb, amax, inv);
+  } else if (sm == 1 && (M % 2) == 0 && (sn % 2) == 0 && (sh % 2) == 0 && (sw % 2) == 0 &&
+             (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+    cg::stage_xt_vec2_kernel<T><<<grid, 256, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
+                                                             bias_rows, sumsq, qpb, amax, inv);
+  } else {
+    cg::stage_xt_kernel<T><<<grid, block, 0, S(stream)>>>(src, sn, sm, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
+                                                          bias_rows, sumsq, qpb, amax, inv);
+  }
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int stage_yt_t(const float* src, long long sn, long long sc, long long sh, long long sw, int B, const cg_unfold_geom* g,
+               const cg_cl_plan* plan, float scale, T* dst, int n_slots_total, int slot0, unsigned int* amax,
+               float* inv, cg_stream_t stream) {
+  if (!g || !plan) return fail("null argument");
+  if (B <= 0) return 0;
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  const int n_planes = plan->n_rh * plan->n_rw;
+  constexpr int kCW = 128 / sizeof(T), kLPP = kCW / 4;      // channels per chunk row, lanes per position
+  if (plan->cw != kCW) return fail("plan chunk width %d does not match the staged element type", plan->cw);
+  const int n_cb = plan->Cp / kCW;
+  if ((B + cg::kYtSamples - 1) / cg::kYtSamples > 65535 || n_planes * n_cb > 65535)
+    return fail("problem too large for the staging grid");
+  if (sizeof(T) == 2 && (!amax || !inv)) return fail("FP16 staging needs the amax scratch and the inverse-scale output");
+  cg::YtParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;
+  p.sn = sn; p.sc = sc; p.sh_ = sh; p.sw_ = sw;
+  p.Cs = plan->Cs; p.n_cb = n_cb; p.merged = plan->merged; p.KW = g->KW; p.dw = g->dw; p.pw = g->pw;
+  p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sth = g->sh; p.stw = g->sw;
+  p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
+  for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
+  p.scale = scale; p.slot0 = slot0;
+  p.slot_stride = plan->slot_stride;
+  p.chunk_stride = plan->slot_stride * n_slots_total;
+  const int n_pos = plan->Hs * plan->Ws;
+  const long long extent = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1) * sh +
+                           static_cast<long long>(g->W - 1 + g->KW * g->dw) * sw;
+  if (sc < 0 || sh < 0 || sw < 0 || extent >= (1LL << 31) || plan->slot_stride >= (1LL << 31))
+    return fail("cg_stage_yt: one sample must span fewer than 2^31 elements with non-negative strides");
+  const bool vec4 = !plan->merged && sc == 1 && (g->C % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (sizeof(T) == 2) {
+    // single pass when the sample is a dense NHWC block that a cluster of <= 8 CTAs can hold in registers
+    const int parts = fused_parts(static_cast<long long>(g->C) * g->H * g->W);
+    const int cvn = g->C / 4;
+    if (fused_enabled() && vec4 && sw == g->C && sh == static_cast<long long>(g->W) * g->C && parts > 0 && B <= (1 << 24) &&
+        cvn <= cg::kFusedThreads && (cg::kFusedThreads % cvn) == 0 && g->H <= cg::kYtFusedMaxDim &&
+        g->W <= cg::kYtFusedMaxDim) {
+      if (launch_clustered(cg::stage_yt_fused_kernel, B * parts, parts, stream, src, p, reinterpret_cast<__half*>(dst), inv,
+                           parts)) return 1;
+      CG_LAUNCH_CHECK();
+      return 0;
+    }
+    if (sample_absmax(src, sn, sc, sh, sw, B, g->C, g->H, g->W, amax, slot0, d.sm, stream)) return 1;
+  }
+  // threads = kLPP lanes per position; small window grids get a block that covers them in k equal steps
+  // (36 positions -> 288 threads x 1 step, 100 -> 416 x 2) instead of idling most of a 256-thread block
+  int threads = 256, ppb = 128;
+  if (n_pos < 128) {
+    int k = 1;
+    while (kLPP * ((n_pos + k - 1) / k) > 512) ++k;
+    threads = (kLPP * ((n_pos + k - 1) / k) + 31) / 32 * 32;
+    ppb = n_pos;
+  }
+  dim3 grid((n_pos + ppb - 1) / ppb, (B + cg::kYtSamples - 1) / cg::kYtSamples, n_planes * n_cb);
+  if (vec4) cg::stage_yt_kernel<true, T><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb, amax, inv);
+  else cg::stage_yt_kernel<false, T><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb, amax, inv);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool kHalf>
+int ghost_norm_t(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, int sm_count,
+                        cg_stream_t stream) {
+  const int Q = g->Ho * g->Wo;
+  cg::GhostParams p;
+  memset(&p, 0, sizeof(p));
+  p.Q = Q; p.ns = 128 / Q; p.O = d->O; p.C = g->C; p.KH = g->KH; p.KW = g->KW;
+  for (int t = 0; t < g->KH * g->KW; ++t) {
+    p.tap_plane[t] = plan->tap_plane[t]; p.tap_hoff[t] = plan->tap_hoff[t]; p.tap_woff[t] = plan->tap_woff[t];
+  }
+  p.slot0 = d->slot0; p.n_slots = d->n_slots;
+  p.n_items = (d->n_slots + p.ns - 1) / p.ns;
+  p.norm2 = d->norm2;
+  p.inv_x = d->inv_x; p.inv_y = d->inv_y;
+  // K-major tiles: 128 rows of one 128-byte chunk (32 TF32 / 64 FP16 channels), SWIZZLE_128B
+  constexpr cuuint32_t cw = kHalf ? 64 : 32;
+  if (plan->cw != static_cast<int>(cw)) return fail("plan chunk width %d does not match the operand type", plan->cw);
+  const cuuint64_t rb = 128;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  const cuuint64_t slot_bytes = static_cast<cuuint64_t>(plan->slot_stride) * (kHalf ? 2 : 4);
+
+  CUtensorMap tx, ty;
+  {
+    // Xt[o/cw][row][o%cw]: a K-major tile = 128 rows of one chunk
+    cuuint64_t dims[3] = {cw, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->O + cw - 1) / cw)};
+    cuuint64_t str[2] = {rb, static_cast<cuuint64_t>(d->xt_rows) * rb};
+    cuuint32_t box[3] = {cw, 128, 1};
+    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box, sw, kHalf)) return 1;
+  }
+  const cuuint64_t n_cb = (g->C + cw - 1) / cw;
+  cuuint64_t ydims[5] = {cw, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
+                         static_cast<cuuint64_t>(d->n_slots_total),
+                         static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * n_cb};
+  cuuint64_t ystr[4] = {rb, rb * plan->Ws, slot_bytes, slot_bytes * d->n_slots_total};
+  const int npos = plan->Hs * plan->Ws;
+  static const bool force_v1 = [] { const char* e = getenv("CSLGAN_GHOST_V1"); return e && e[0] == '1'; }();
+  if (npos <= 128 && plan->Ws <= 256 && plan->Hs <= 256 && !force_v1) {
+    // Gram of the un-shifted planes + tap gather in the epilogue (ghost2.cuh)
+    cg::Ghost2Params q;
+    memset(&q, 0, sizeof(q));
+    q.Q = Q; q.ns = 128 / Q; q.Wo = g->Wo; q.O = d->O; q.C = g->C;
+    q.n_planes = plan->n_rh * plan->n_rw; q.Hs = plan->Hs; q.Ws = plan->Ws; q.npos = npos;
+    q.spp = 128 / npos < q.ns ? 128 / npos : q.ns;
+    q.n_sub = (q.ns + q.spp - 1) / q.spp;
+    int n = 0;
+    for (int pl = 0; pl < q.n_planes; ++pl) {
+      q.plane_tap0[pl] = n;
+      for (int t = 0; t < g->KH * g->KW; ++t)
+        if (plan->tap_plane[t] == pl) q.tap_shift[n++] = plan->tap_hoff[t] * plan->Ws + plan->tap_woff[t];
+    }
+    q.plane_tap0[q.n_planes] = n;
+    q.slot0 = d->slot0; q.n_slots = d->n_slots; q.n_items = p.n_items; q.norm2 = d->norm2;
+    q.inv_x = d->inv_x; q.inv_y = d->inv_y;
+    cuuint32_t box[5] = {cw, static_cast<cuuint32_t>(plan->Ws), static_cast<cuuint32_t>(plan->Hs),
+                         static_cast<cuuint32_t>(q.spp), 1};
+    if (make_tmap_nd(&ty, d->Yt, 5, ydims, ystr, box, sw, kHalf)) return 1;
+    const int smem = cg::g2_smem_bytes(Q);
+    CG_CHECK(cudaFuncSetAttribute(cg::ghost2_norm_kernel<kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid2 = d->max_ctas > 0 ? d->max_ctas : sm_count;
+    if (grid2 > q.n_items) grid2 = q.n_items;
+    cg::ghost2_norm_kernel<kHalf><<<grid2, cg::kG2Threads, smem, S(stream)>>>(tx, ty, q);
+    CG_LAUNCH_CHECK();
+    return 0;
+  }
+  {
+    cuuint32_t box[5] = {cw, static_cast<cuuint32_t>(g->Wo), static_cast<cuuint32_t>(g->Ho),
+                         static_cast<cuuint32_t>(p.ns), 1};
+    if (make_tmap_nd(&ty, d->Yt, 5, ydims, ystr, box, sw, kHalf)) return 1;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::ghost_norm_kernel<kHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kGSmemBytes));
+    attr_set[dev] = true;
+  }
+  int grid = d->max_ctas > 0 ? d->max_ctas : sm_count;
+  if (grid > p.n_items) grid = p.n_items;
+  cg::ghost_norm_kernel<kHalf><<<grid, cg::kGThreads, cg::kGSmemBytes, S(stream)>>>(tx, ty, p);
   CG_LAUNCH_CHECK();
   return 0;
 }
@@ -377,8 +690,11 @@ int cg_contract(const cg_contract_desc* d, cg_stream_t stream) {
   return 0;
 }
 
-int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan) {
+int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan) { return cg_plan_cl_cw(g, merged, 32, plan); }
+
+int cg_plan_cl_cw(const cg_unfold_geom* g, int merged, int cw, cg_cl_plan* plan) {
   if (!g || !plan) return fail("null argument");
+  if (cw != 32 && cw != 64) return fail("chunk width must be 32 (TF32) or 64 (FP16) channels");
   if (g->KH < 1 || g->KH > CG_MAX_KH || g->KW < 1 || g->KW > CG_MAX_KH) return fail("unsupported filter size");
   if (g->sh < 1 || g->sw < 1 || g->dh < 1 || g->dw < 1) return fail("stride/dilation must be >= 1");
   memset(plan, 0, sizeof(*plan));
@@ -413,8 +729,9 @@ int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan) {
         plan->tap_woff[t] = aw[kw] - aw_min;
       }
   }
-  plan->Cp = (plan->Cs + 31) / 32 * 32;
-  plan->slot_stride = static_cast<long long>(plan->Hs) * plan->Ws * 32;   // per 32-channel chunk
+  plan->cw = cw;
+  plan->Cp = (plan->Cs + cw - 1) / cw * cw;
+  plan->slot_stride = static_cast<long long>(plan->Hs) * plan->Ws * cw;   // elements per slot inside one chunk
   return 0;
 }
 
@@ -423,7 +740,7 @@ int cg_plan_ghost(const cg_unfold_geom* g, cg_ghost_plan* plan) {
   const int Q = g->Ho * g->Wo;
   if (Q < 1 || Q > 128 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128 (got %d)", Q);
   if (g->Wo > 256 || g->Ho > 256) return fail("window extent too large for a TMA box");
-  return cg_plan_cl(g, 0, plan);
+  return cg_plan_cl_cw(g, 0, 32, plan);
 }
 
 int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghost_plan* plan, cg_stream_t stream) {
@@ -434,203 +751,124 @@ int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghos
   if (d->n_slots <= 0) return 0;
   const int Q = g->Ho * g->Wo;
   if (Q < 1 || (128 % Q) != 0) return fail("ghost norms need Ho*Wo to divide 128");
-  cg::GhostParams p;
-  memset(&p, 0, sizeof(p));
-  p.Q = Q; p.ns = 128 / Q; p.O = d->O; p.C = g->C; p.KH = g->KH; p.KW = g->KW;
-  for (int t = 0; t < g->KH * g->KW; ++t) {
-    p.tap_plane[t] = plan->tap_plane[t]; p.tap_hoff[t] = plan->tap_hoff[t]; p.tap_woff[t] = plan->tap_woff[t];
-  }
-  p.slot0 = d->slot0; p.n_slots = d->n_slots;
-  p.n_items = (d->n_slots + p.ns - 1) / p.ns;
-  p.norm2 = d->norm2;
+  if (d->half && (!d->inv_x || !d->inv_y)) return fail("cg_ghost_norm: FP16 operands need inv_x / inv_y");
+  return d->half ? ghost_norm_t<true>(d, g, plan, dv.sm, stream) : ghost_norm_t<false>(d, g, plan, dv.sm, stream);
+}
 
-  CUtensorMap tx, ty;
-  {
-    // Xt[o/32][row][o%32]: a K-major tile = 128 rows of one 32-channel chunk
-    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->O + 31) / 32)};
-    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
-    cuuint32_t box[3] = {32, 128, 1};
-    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box)) return 1;
-  }
-  const int npos = plan->Hs * plan->Ws;
-  static const bool force_v1 = [] { const char* e = getenv("CSLGAN_GHOST_V1"); return e && e[0] == '1'; }();
-  if (npos <= 128 && plan->Ws <= 256 && plan->Hs <= 256 && !force_v1) {
-    // Gram of the un-shifted planes + tap gather in the epilogue (ghost2.cuh)
-    cg::Ghost2Params q;
-    memset(&q, 0, sizeof(q));
-    q.Q = Q; q.ns = 128 / Q; q.Wo = g->Wo; q.O = d->O; q.C = g->C;
-    q.n_planes = plan->n_rh * plan->n_rw; q.Hs = plan->Hs; q.Ws = plan->Ws; q.npos = npos;
-    q.spp = 128 / npos < q.ns ? 128 / npos : q.ns;
-    q.n_sub = (q.ns + q.spp - 1) / q.spp;
-    int n = 0;
-    for (int pl = 0; pl < q.n_planes; ++pl) {
-      q.plane_tap0[pl] = n;
-      for (int t = 0; t < g->KH * g->KW; ++t)
-        if (plan->tap_plane[t] == pl) q.tap_shift[n++] = plan->tap_hoff[t] * plan->Ws + plan->tap_woff[t];
-    }
-    q.plane_tap0[q.n_planes] = n;
-    q.slot0 = d->slot0; q.n_slots = d->n_slots; q.n_items = p.n_items; q.norm2 = d->norm2;
-    {
-      const cuuint64_t n_cb = (g->C + 31) / 32;
-      cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
-                            static_cast<cuuint64_t>(d->n_slots_total),
-                            static_cast<cuuint64_t>(q.n_planes) * n_cb};
-      cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
-                           static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
-      cuuint32_t box[5] = {32, static_cast<cuuint32_t>(plan->Ws), static_cast<cuuint32_t>(plan->Hs),
-                           static_cast<cuuint32_t>(q.spp), 1};
-      if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box)) return 1;
-    }
-    const int smem = cg::g2_smem_bytes(Q);
-    CG_CHECK(cudaFuncSetAttribute(cg::ghost2_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int grid2 = d->max_ctas > 0 ? d->max_ctas : dv.sm;
-    if (grid2 > q.n_items) grid2 = q.n_items;
-    cg::ghost2_norm_kernel<<<grid2, cg::kG2Threads, smem, S(stream)>>>(tx, ty, q);
-    CG_LAUNCH_CHECK();
+// k-block geometry of the channels-last path for k-blocks of KB contraction rows; non-zero = not tileable
+static int cl_kblock_kb(const cg_unfold_geom* g, int per_sample, int KB, int min_rows, int* kb_rows, int* kb_w,
+                        int* kb_h, int* kb_s) {
+  const int Q = g->Ho * g->Wo;
+  if (Q >= KB) {
+    if (Q % KB) return 1;
+    const int w = g->Wo < KB ? g->Wo : KB;
+    if (g->Wo % w || KB % w) return 1;
+    *kb_w = w; *kb_h = KB / w; *kb_s = 1; *kb_rows = KB;
+    if (g->Ho % *kb_h) return 1;
     return 0;
   }
-  {
-    const cuuint64_t n_cb = (g->C + 31) / 32;
-    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
-                          static_cast<cuuint64_t>(d->n_slots_total),
-                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * n_cb};
-    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
-                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
-    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(g->Wo), static_cast<cuuint32_t>(g->Ho),
-                         static_cast<cuuint32_t>(p.ns), 1};
-    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box)) return 1;
+  if (KB % Q) return 1;
+  *kb_w = g->Wo; *kb_h = g->Ho;
+  if (per_sample) {
+    if (Q % min_rows) return 1;
+    *kb_s = 1; *kb_rows = Q;
+  } else {
+    if (KB / Q > 32) return 1;               // slot ranges are 32-aligned (Bpad), not more
+    *kb_s = KB / Q; *kb_rows = KB;
   }
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CG_CHECK(cudaGetDevice(&dev));
-  if (!attr_set[dev]) {
-    CG_CHECK(cudaFuncSetAttribute(cg::ghost_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kGSmemBytes));
-    attr_set[dev] = true;
-  }
-  int grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
-  if (grid > p.n_items) grid = p.n_items;
-  cg::ghost_norm_kernel<<<grid, cg::kGThreads, cg::kGSmemBytes, S(stream)>>>(tx, ty, p);
-  CG_LAUNCH_CHECK();
   return 0;
 }
 
-// k-block geometry of the channels-last path; returns non-zero when the window grid cannot be tiled
-static int cl_kblock(const cg_unfold_geom* g, int per_sample, int* kb_rows, int* kb_w, int* kb_h, int* kb_s) {
+// FP16 operands use k-blocks of 64 rows where the window grid allows (the single-thread TMA / MMA roles pay a fixed
+// cost per k-block that is comparable with 32 rows of FP16 MMA time), 32 rows otherwise; TF32 always 32.
+static int cl_kblock(const cg_unfold_geom* g, int per_sample, int* kb_rows, int* kb_w, int* kb_h, int* kb_s,
+                     int half = 0) {
+  const int min_rows = half ? 16 : 8;
+  if (half && cl_kblock_kb(g, per_sample, 64, min_rows, kb_rows, kb_w, kb_h, kb_s) == 0) return 0;
+  if (cl_kblock_kb(g, per_sample, 32, min_rows, kb_rows, kb_w, kb_h, kb_s) == 0) return 0;
   const int Q = g->Ho * g->Wo;
-  if (Q >= 32) {
-    if (Q % 32) return fail("channels-last path needs Ho*Wo to be a multiple of 32 or a divisor of 32 (got %d)", Q);
-    int w = g->Wo < 32 ? g->Wo : 32;
-    if (g->Wo % w || 32 % w) return fail("window row length %d cannot be tiled into 32-position k-blocks", g->Wo);
-    *kb_w = w; *kb_h = 32 / w; *kb_s = 1; *kb_rows = 32;
-    if (g->Ho % *kb_h) return fail("window grid %dx%d cannot be tiled into 32-position k-blocks", g->Ho, g->Wo);
-    return 0;
-  }
-  if (32 % Q) return fail("channels-last path needs Ho*Wo to be a multiple of 32 or a divisor of 32 (got %d)", Q);
-  *kb_w = g->Wo; *kb_h = g->Ho;
-  if (per_sample) {
-    if (Q % 8) return fail("per-sample groups need Ho*Wo to be a multiple of 8 (got %d)", Q);
-    *kb_s = 1; *kb_rows = Q;
-  } else {
-    *kb_s = 32 / Q; *kb_rows = 32;
-  }
-  return 0;
+  return fail("channels-last path cannot tile a %dx%d window grid (Q = %d) into k-blocks%s", g->Ho, g->Wo, Q,
+              per_sample ? " (per-sample groups need a multiple of 8 / 16 positions)" : "");
+}
+
+int cg_cl_kblock_rows(const cg_unfold_geom* g, int half, int* kb_rows, int* kb_s) {
+  if (!g || !kb_rows || !kb_s) return fail("null argument");
+  int w, h;
+  return cl_kblock(g, 0, kb_rows, &w, &h, kb_s, half);
 }
 
 int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M, int Ho,
                 int Wo, float scale, float* dst, long long rows_total, int slot0, float* bias_rows, float* sumsq,
                 cg_stream_t stream) {
-  if (B <= 0 || M <= 0) return 0;
+  return stage_xt_t<float>(src, sn, sm, sh, sw, B, M, Ho, Wo, scale, dst, rows_total, slot0, bias_rows, sumsq, nullptr,
+                           nullptr, stream);
+}
 
-  DevInfo d;
-  if (dev_info(&d)) return 1;
-  const int Q = Ho * Wo;
-  if (bias_rows) CG_CHECK(cudaMemsetAsync(bias_rows + static_cast<long long>(slot0) * M, 0, sizeof(float) * B * M, S(stream)));
-  if (sumsq) CG_CHECK(cudaMemsetAsync(sumsq + slot0, 0, sizeof(float) * B, S(stream)));
-  if (static_cast<long long>(slot0 + B) * Q > rows_total) return fail("Xt too small for slots [%d, %d)", slot0, slot0 + B);
-  int block = ((M < 256 ? M : 256) + 31) / 32 * 32;
-  // positions per block: keep ~8 blocks per SM in flight without shredding the bias sums into atomics
-  int qchunks = static_cast<int>((8LL * d.sm + B - 1) / B);
-  if (qchunks < 1) qchunks = 1;
-  if (qchunks > Q) qchunks = Q;
-  int qpb = (Q + qchunks - 1) / qchunks;
-  dim3 grid(B, (Q + qpb - 1) / qpb);             // batch on grid.x (no 65535 limit), position chunks on grid.y
-  const bool vec4 = sm == 1 && (M % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
-                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-  if (vec4) {
-    const int mv = M / 4;
-    int vblock = 256;                                         // rows wider than 1024 channels: block-sized strips
-    if (mv <= 256) {
-      vblock = mv >= 128 ? ((mv + 31) / 32 * 32) : 128;       // at least 128 threads: several positions in parallel
-      if (vblock % mv) vblock = (vblock / mv + 1) * mv;       // whole groups of channel vectors
-      if (vblock > 1024) vblock = mv;
-    }
-    if (mv > 256)
-      cg::stage_xt_vec4_wide_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
-                                                                     slot0, bias_rows, sumsq, qpb);
-    else
-      cg::stage_xt_vec4_kernel<<<grid, vblock, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total,
-                                                                      slot0, bias_rows, sumsq, qpb);
-  } else if (sm == 1 && (M % 2) == 0 && (sn % 2) == 0 && (sh % 2) == 0 && (sw % 2) == 0 &&
-             (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-    cg::stage_xt_vec2_kernel<<<grid, 256, 0, S(stream)>>>(src, sn, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
-                                                          bias_rows, sumsq, qpb);
-  } else {
-    cg::stage_xt_kernel<<<grid, block, 0, S(stream)>>>(src, sn, sm, sh, sw, M, Wo, Q, scale, dst, rows_total, slot0,
-                                                       bias_rows, sumsq, qpb);
-  }
-  CG_LAUNCH_CHECK();
-  return 0;
+int cg_stage_xt_h(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M, int Ho,
+                  int Wo, float scale, void* dst_half, long long rows_total, int slot0, float* bias_rows, float* sumsq,
+                  unsigned int* amax, float* inv, cg_stream_t stream) {
+  return stage_xt_t<__half>(src, sn, sm, sh, sw, B, M, Ho, Wo, scale, static_cast<__half*>(dst_half), rows_total, slot0,
+                            bias_rows, sumsq, amax, inv, stream);
 }
 
 int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
                 const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, float* dst, int n_slots_total,
                 int slot0, cg_stream_t stream) {
-  if (!g || !plan) return fail("null argument");
-  if (B <= 0) return 0;
+  return stage_yt_t<float>(src, sn, sc, sh, sw, B, g, plan, scale, dst, n_slots_total, slot0, nullptr, nullptr, stream);
+}
+
+int cg_stage_yt_h(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
+                  const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, void* dst_half, int n_slots_total,
+                  int slot0, unsigned int* amax, float* inv, cg_stream_t stream) {
+  return stage_yt_t<__half>(src, sn, sc, sh, sw, B, g, plan, scale, static_cast<__half*>(dst_half), n_slots_total,
+                            slot0, amax, inv, stream);
+}
+
+int cg_clip_mult(const float* factor, const float* inv_x, const float* inv_y, int slot_lo, int slot_hi, float* mult,
+                 float* out_scale, cg_stream_t stream) {
+  if (slot_hi <= slot_lo) return 0;
+  if (!factor || !inv_x || !inv_y || !mult || !out_scale) return fail("null argument");
+  const int n = slot_hi - slot_lo;
+  if (n <= 8192) {
+    cg::clip_mult_kernel<<<1, 1024, 0, S(stream)>>>(factor, inv_x, inv_y, slot_lo, slot_hi, mult, out_scale);
+    CG_LAUNCH_CHECK();
+    return 0;
+  }
+  // many slots: two multi-block stages meeting in out_scale[1] (raw maximum)
+  unsigned int* raw = reinterpret_cast<unsigned int*>(out_scale + 1);
+  CG_CHECK(cudaMemsetAsync(raw, 0, sizeof(unsigned int), S(stream)));
+  const int blocks = (n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592;
+  cg::clip_mult_stage1_kernel<<<blocks, 256, 0, S(stream)>>>(factor, inv_x, inv_y, slot_lo, slot_hi, mult, raw);
+  CG_LAUNCH_CHECK();
+  cg::clip_mult_stage2_kernel<<<blocks, 256, 0, S(stream)>>>(slot_lo, slot_hi, mult, raw, out_scale);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_scale_slots_h(const void* src_half, void* dst_half, int rows, long long pitch, long long slot_stride, int slot_lo,
+                     int slot_hi, const float* mult, cg_stream_t stream) {
+  if (rows <= 0 || slot_hi <= slot_lo) return 0;
   DevInfo d;
   if (dev_info(&d)) return 1;
-  const int n_planes = plan->n_rh * plan->n_rw;
-  const int n_cb = plan->Cp / 32;
-  if ((B + cg::kYtSamples - 1) / cg::kYtSamples > 65535 || n_planes * n_cb > 65535)
-    return fail("problem too large for the staging grid");
-  cg::YtParams p;
-  memset(&p, 0, sizeof(p));
-  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;
-  p.sn = sn; p.sc = sc; p.sh_ = sh; p.sw_ = sw;
-  p.Cs = plan->Cs; p.n_cb = n_cb; p.merged = plan->merged; p.KW = g->KW; p.dw = g->dw; p.pw = g->pw;
-  p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sth = g->sh; p.stw = g->sw;
-  p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
-  for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
-  p.scale = scale; p.slot0 = slot0;
-  p.slot_stride = plan->slot_stride;
-  p.chunk_stride = plan->slot_stride * n_slots_total;
-  const int n_pos = plan->Hs * plan->Ws;
-  const long long extent = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1) * sh +
-                           static_cast<long long>(g->W - 1 + g->KW * g->dw) * sw;
-  if (sc < 0 || sh < 0 || sw < 0 || extent >= (1LL << 31) || plan->slot_stride >= (1LL << 31))
-    return fail("cg_stage_yt: one sample must span fewer than 2^31 elements with non-negative strides");
-  const bool vec4 = !plan->merged && sc == 1 && (g->C % 4) == 0 && (sn % 4) == 0 && (sh % 4) == 0 && (sw % 4) == 0 &&
-                    (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-  // threads = 8 lanes per position; small window grids get a block that covers them in k equal steps
-  // (36 positions -> 288 threads x 1 step, 100 -> 416 x 2) instead of idling most of a 256-thread block
-  int threads = 256, ppb = 128;
-  if (n_pos < 128) {
-    int k = 1;
-    while (8 * ((n_pos + k - 1) / k) > 512) ++k;
-    threads = (8 * ((n_pos + k - 1) / k) + 31) / 32 * 32;
-    ppb = n_pos;
-  }
-  dim3 grid((n_pos + ppb - 1) / ppb, (B + cg::kYtSamples - 1) / cg::kYtSamples, n_planes * n_cb);
-  if (vec4) cg::stage_yt_kernel<true><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb);
-  else cg::stage_yt_kernel<false><<<grid, threads, 0, S(stream)>>>(src, p, dst, ppb);
+  if (slot_stride > 0x7fffffffLL) return fail("slot_stride too large");
+  if (slot_stride % 8 || pitch % 8 || (reinterpret_cast<uintptr_t>(src_half) & 15) || (reinterpret_cast<uintptr_t>(dst_half) & 15))
+    return fail("cg_scale_slots_h needs 16-byte aligned rows and slot strides");
+  const long long work = static_cast<long long>(slot_hi - slot_lo) * slot_stride / 8;
+  long long gx = (work + 255) / 256;
+  const long long want = (static_cast<long long>(d.sm) * 8 + rows - 1) / rows;   // ~8 blocks per SM overall
+  if (gx > want) gx = want;
+  if (gx < 1) gx = 1;
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(rows < 65535 ? rows : 65535));
+  cg::scale_slots_half_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __half*>(src_half),
+                                                           static_cast<__half*>(dst_half), rows, pitch,
+                                                           static_cast<int>(slot_stride), slot_lo, slot_hi, mult);
   CG_LAUNCH_CHECK();
   return 0;
 }
 
 int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan) {
   if (!g || !plan) return 0;
-  const int n_cb = plan->Cp / 32;
-  return (M >= 256 && M % 256 == 0 && n_cb >= 4 && n_cb % 4 == 0 && !plan->merged) ? 1 : 0;
+  return (M >= 256 && M % 256 == 0 && plan->Cp >= 128 && plan->Cp % 128 == 0 && !plan->merged) ? 1 : 0;
 }
 
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream) {
@@ -641,21 +879,24 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   if (d->n_groups <= 0) return 0;
   const int Q = g->Ho * g->Wo;
   int kb_rows, kb_w, kb_h, kb_s;
-  if (cl_kblock(g, d->group_mode == CG_GROUP_SAMPLE, &kb_rows, &kb_w, &kb_h, &kb_s)) return 1;
+  if (cl_kblock(g, d->group_mode == CG_GROUP_SAMPLE, &kb_rows, &kb_w, &kb_h, &kb_s, d->half)) return 1;
   cg::ClParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->M; p.n_mtiles = (d->M + 127) / 128;
-  p.C = plan->Cs; p.n_cb = plan->Cp / 32;
+  const int cw = d->half ? 64 : 32;                  // channels per 128-byte chunk row
+  const int maxc = 256 / cw;                         // chunks of a 256-column tile
+  if (plan->cw != cw) return fail("plan chunk width %d does not match the operand type", plan->cw);
+  p.C = plan->Cs; p.n_cb = plan->Cp / cw;
   p.n_taps = plan->n_taps;
-  if (p.n_cb >= 8) {
-    // wide layers: a tile is up to 8 chunks of ONE tap (one TMA box)
-    const int parts = (p.n_cb + 7) / 8;
+  if (p.n_cb >= maxc) {
+    // wide layers: a tile is up to 256 columns of ONE tap (one TMA box)
+    const int parts = (p.n_cb + maxc - 1) / maxc;
     p.tpt = 1; p.cpt = (p.n_cb + parts - 1) / parts;
     p.tiles_per_tap = (p.n_cb + p.cpt - 1) / p.cpt;
     p.n_nt = p.n_taps * p.tiles_per_tap;
   } else {
-    // narrow layers: a tile stacks whole taps (one TMA box each) up to 8 chunks
-    int tpt = 8 / p.n_cb;
+    // narrow layers: a tile stacks whole taps (one TMA box each) up to 256 columns
+    int tpt = maxc / p.n_cb;
     if (tpt > p.n_taps) tpt = p.n_taps;
     const int parts = (p.n_taps + tpt - 1) / tpt;
     p.tpt = (p.n_taps + parts - 1) / parts; p.cpt = p.n_cb;
@@ -666,7 +907,7 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
     p.tap_plane[t] = plan->tap_plane[t]; p.tap_hoff[t] = plan->tap_hoff[t]; p.tap_woff[t] = plan->tap_woff[t];
   }
   p.Q = Q; p.Wo = g->Wo; p.kb_rows = kb_rows; p.kb_s = kb_s;
-  p.nkb_slot = (Q >= 32) ? Q / 32 : 1;
+  p.nkb_slot = (Q >= kb_rows) ? Q / kb_rows : 1;
   p.group_mode = d->group_mode; p.n_groups = d->n_groups; p.slot_lo = d->slot_lo;
   p.n_seg = d->n_seg > 0 ? d->n_seg : 1;
   p.seg_stride = d->seg_stride;
@@ -689,43 +930,22 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   p.KH = g->KH; p.KW = g->KW; p.Corig = g->C; p.merged = plan->merged;
   p.n_items = static_cast<long long>(p.n_groups) * p.n_nt * p.n_mtiles;
 
+  if (d->half) {
+    if (d->group_mode == CG_GROUP_SAMPLE) {
+      if (!d->inv_x || !d->inv_y) return fail("cg_cl_contract: FP16 per-sample groups need inv_x / inv_y");
+      if (p.n_seg > 1) return fail("cg_cl_contract: FP16 operands cannot sum passes per sample (staging scales differ)");
+    }
+    p.inv_x = d->inv_x; p.inv_y = d->inv_y; p.out_scale = d->out_scale;
+  }
   if (d->pair) {
-    if (!cg_cl_pair_ok(d->M, g, plan) || d->group_mode != CG_GROUP_SPLITK || d->epi != CG_EPI_ACCUM || kb_rows != 32)
+    if (!cg_cl_pair_ok(d->M, g, plan) || d->group_mode != CG_GROUP_SPLITK || d->epi != CG_EPI_ACCUM ||
+        (kb_rows != 32 && kb_rows != 64))
       return fail("cg_cl_contract: pair = 1 needs a split-K clipped sum with M %% 256 == 0 and 128-channel multiples");
-    return launch_pair(d, g, plan, p, kb_w, kb_h, kb_s, stream);
+    return d->half ? launch_pair_t<true>(d, plan, p, kb_rows, kb_w, kb_h, kb_s, stream)
+                   : launch_pair_t<false>(d, plan, p, kb_rows, kb_w, kb_h, kb_s, stream);
   }
-
-  CUtensorMap tx, ty;
-  {
-    // Xt[m/32][row][m%32]: one box = kb_rows rows of four consecutive chunks -> smem [chunk][row][32]
-    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(d->xt_rows), static_cast<cuuint64_t>((d->M + 31) / 32)};
-    cuuint64_t str[2] = {128, static_cast<cuuint64_t>(d->xt_rows) * 128};
-    cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kb_rows), 4};
-    if (make_tmap_nd(&tx, d->Xt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-  }
-  {
-    // Yt[plane*n_cb + c/32][slot][hs][ws][c%32]: one box = a tap window of `cpt` consecutive chunks
-    cuuint64_t dims[5] = {32, static_cast<cuuint64_t>(plan->Ws), static_cast<cuuint64_t>(plan->Hs),
-                          static_cast<cuuint64_t>(d->n_slots_total),
-                          static_cast<cuuint64_t>(plan->n_rh * plan->n_rw) * p.n_cb};
-    cuuint64_t str[4] = {128, 128ull * plan->Ws, static_cast<cuuint64_t>(plan->slot_stride) * 4,
-                         static_cast<cuuint64_t>(plan->slot_stride) * 4 * d->n_slots_total};
-    cuuint32_t box[5] = {32, static_cast<cuuint32_t>(kb_w), static_cast<cuuint32_t>(kb_h),
-                         static_cast<cuuint32_t>(kb_s), static_cast<cuuint32_t>(p.cpt)};
-    if (make_tmap_nd(&ty, d->Yt, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-  }
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CG_CHECK(cudaGetDevice(&dev));
-  if (!attr_set[dev]) {
-    CG_CHECK(cudaFuncSetAttribute(cg::cl_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cg::kClSmemBytes));
-    attr_set[dev] = true;
-  }
-  long long grid = d->max_ctas > 0 ? d->max_ctas : dv.sm;
-  if (grid > p.n_items) grid = p.n_items;
-  cg::cl_contract_kernel<<<static_cast<int>(grid), cg::kClThreads, cg::kClSmemBytes, S(stream)>>>(tx, ty, p);
-  CG_LAUNCH_CHECK();
-  return 0;
+  return d->half ? launch_cl_t<true>(d, plan, p, kb_rows, kb_w, kb_h, kb_s, dv.sm, stream)
+                 : launch_cl_t<false>(d, plan, p, kb_rows, kb_w, kb_h, kb_s, dv.sm, stream);
 }
 
 int cg_rowpair_dot(const float* T, long long rows_total, int n_chunks, int row_a, int row_b, int B, float* out,
@@ -750,7 +970,22 @@ int cg_outer_rows_cl(const float* Xt, long long x_rows, const float* Yt, long lo
   if (total <= 0) return 0;
   DevInfo d;
   if (dev_info(&d)) return 1;
-  cg::outer_rows_cl_kernel<<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(Xt, x_rows, Yt, y_rows, M, P, slot0, B, out);
+  cg::outer_rows_cl_kernel<float><<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(Xt, x_rows, Yt, y_rows, M, P, slot0,
+                                                                                     B, nullptr, nullptr, out);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_outer_rows_cl_h(const void* Xt_half, long long x_rows, const void* Yt_half, long long y_rows, int M, int P,
+                       int slot0, int B, const float* inv_x, const float* inv_y, float* out, cg_stream_t stream) {
+  const long long total = static_cast<long long>(B) * M * P;
+  if (total <= 0) return 0;
+  if (!inv_x || !inv_y) return fail("null inverse scales");
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::outer_rows_cl_kernel<__half><<<ew_grid(total, 256, d.sm), 256, 0, S(stream)>>>(
+      static_cast<const __half*>(Xt_half), x_rows, static_cast<const __half*>(Yt_half), y_rows, M, P, slot0, B, inv_x,
+      inv_y, out);
   CG_LAUNCH_CHECK();
   return 0;
 }

@@ -16,29 +16,42 @@
 
 namespace cg {
 
-constexpr int kPairStages = 6;
-constexpr int kPairHalfBytes = 4 * kClBoxBytes;                    // 16 KB: four 32-channel chunks x 32 rows
-constexpr int kPairStageBytes = 2 * kPairHalfBytes;                // X rows of this CTA + this CTA's half of Y
-constexpr int kPairSmemBytes = 1024 + kPairStages * kPairStageBytes + 4 * kClEpiBufFloats * 4 + 256;
+template <bool kHalf>
+struct PairCfg {
+  static constexpr int kBoxBytes = ClCfg<kHalf>::kBoxBytes;          // one 128-byte chunk x 32 (TF32) / 64 (FP16) rows
+  static constexpr int kHalfChunks = 128 / ClCfg<kHalf>::kCW;        // chunks of 128 channels / 128 rows of M
+  static constexpr int kHalfBytes = kHalfChunks * kBoxBytes;         // 16 KB
+  static constexpr int kStageBytes = 2 * kHalfBytes;                 // X rows of this CTA + this CTA's half of Y
+  static constexpr int kStages = 6;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 4 * kClEpiBufFloats * 4 + 256;
+};
 
 struct ClPairParams {
   int M, n_mp;                 // output channels, 256-row tile pairs
-  int C, n_cb;                 // channels per tap, 32-wide chunks per tap (multiple of 4)
-  int n_taps, hpt, n_ht;       // half tiles (one tap x 4 chunks): hpt per tap, n_ht in total
+  int C, n_cb;                 // channels per tap (a multiple of 128), 128-byte chunks per tap
+  int n_taps, hpt, n_ht;       // half tiles (one tap x 128 channels): hpt per tap, n_ht in total
   int n_nt;                    // 256-column tiles = ceil(n_ht / 2)
   int tap_plane[kClMaxTaps], tap_hoff[kClMaxTaps], tap_woff[kClMaxTaps];
-  int Q, Wo, kb_s, nkb_slot;   // as ClParams (k-blocks are always 32 contraction rows here)
+  int Q, Wo, kb_s, nkb_slot;   // as ClParams
+  int kb_rows;                 // contraction rows per k-block: 32, or 64 (FP16)
   int oob_chunk;               // a chunk coordinate past the end of Yt: the box is zero-filled
   long long u_lo, u_hi, upg;
   int n_groups;
   float* out;
   long long ldT;
   long long n_items;
+  const float* out_scale;      // FP16 operands: scalar that undoes the common power of two folded into Xc (else NULL)
 };
 
+template <bool kHalf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads, 1)
 cl_pair_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constant__ CUtensorMap tmap_yt,
                const __grid_constant__ ClPairParams p) {
+  using Cfg = PairCfg<kHalf>;
+  constexpr int kPairStages = Cfg::kStages;
+  constexpr int kPairStageBytes = Cfg::kStageBytes;
+  constexpr int kPairHalfBytes = Cfg::kHalfBytes;
+  const uint32_t box_b = static_cast<uint32_t>(p.kb_rows) * 128u;     // bytes of one chunk of a k-block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_buf = reinterpret_cast<float*>(tiles + kPairStages * kPairStageBytes);
@@ -83,31 +96,42 @@ cl_pair_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constan
         int chunk = p.oob_chunk, hoff = 0, woff = 0;
         if (h < p.n_ht) {
           const int tap = h / p.hpt;
-          chunk = p.tap_plane[tap] * p.n_cb + (h - tap * p.hpt) * 4;
+          chunk = p.tap_plane[tap] * p.n_cb + (h - tap * p.hpt) * Cfg::kHalfChunks;
           hoff = p.tap_hoff[tap]; woff = p.tap_woff[tap];
         }
-        for (long long u = u0; u < u1; ++u) {
-          int slot, q0;
-          if (p.kb_s > 1) { slot = static_cast<int>(u) * p.kb_s; q0 = 0; }
-          else { slot = static_cast<int>(u / p.nkb_slot); q0 = static_cast<int>(u - static_cast<long long>(slot) * p.nkb_slot) * 32; }
+        // one division for the first k-block of the item, incremental (slot, q0, oh0, ow0) afterwards: this loop is
+        // the producer's critical path
+        int slot, q0;
+        if (p.kb_s > 1) { slot = static_cast<int>(u0) * p.kb_s; q0 = 0; }
+        else { slot = static_cast<int>(u0 / p.nkb_slot); q0 = static_cast<int>(u0 - static_cast<long long>(slot) * p.nkb_slot) * p.kb_rows; }
+        int oh0 = q0 / p.Wo, ow0 = q0 - oh0 * p.Wo;
+        const int n_u = static_cast<int>(u1 - u0);
+        const int xchunk = (2 * mp + static_cast<int>(rank)) * Cfg::kHalfChunks;
+        for (int iu = 0; iu < n_u; ++iu) {
           uint8_t* xs = tiles + stage * kPairStageBytes;
           const uint32_t full0 = mapa_u32(&full_bar[stage], 0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (lane == 0) {
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);   // both CTAs' boxes
-            tma_load_3d_pair(xs, &tmap_xt, full0, 0, slot * p.Q + q0, (2 * mp + static_cast<int>(rank)) * 4);
+            if (leader) mbar_expect_tx(&full_bar[stage], 4u * Cfg::kHalfChunks * box_b);   // both CTAs' X and Y boxes
+            tma_load_3d_pair(xs, &tmap_xt, full0, 0, slot * p.Q + q0, xchunk);
           } else {
-            const int oh0 = q0 / p.Wo, ow0 = q0 - oh0 * p.Wo;
             tma_load_5d_pair(xs + kPairHalfBytes, &tmap_yt, full0, 0, woff + ow0, hoff + oh0, slot, chunk);
           }
           if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+          if (p.kb_s > 1) {
+            slot += p.kb_s;
+          } else {
+            q0 += p.kb_rows;
+            if (q0 >= p.Q) { q0 = 0; oh0 = 0; ow0 = 0; ++slot; }
+            else { ow0 += p.kb_rows; while (ow0 >= p.Wo) { ow0 -= p.Wo; ++oh0; } }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32_mn(256, 256);
+      const uint32_t idesc = umma_idesc_mn<kHalf>(256, 256);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (long long item = pair_id; item < p.n_items; item += n_pairs) {
         const long long t = item / p.n_mp;
@@ -123,12 +147,13 @@ cl_pair_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t xs = smem_u32(tiles + stage * kPairStageBytes);
-          const uint64_t adesc = umma_desc_mn_sw128(xs, kClBoxBytes);
-          const uint64_t bdesc = umma_desc_mn_sw128(xs + kPairHalfBytes, kClBoxBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32_pair(tmem_d, adesc + static_cast<uint64_t>(64 * k), bdesc + static_cast<uint64_t>(64 * k), idesc,
-                           (first && k == 0) ? 0u : 1u);
+          const uint64_t adesc = umma_desc_mn<kHalf>(xs, box_b);
+          const uint64_t bdesc = umma_desc_mn<kHalf>(xs + kPairHalfBytes, box_b);
+          constexpr uint64_t kAdv = ClCfg<kHalf>::kKRows * 128 / 16;
+          const int n_k = p.kb_rows / ClCfg<kHalf>::kKRows;
+#pragma unroll 4
+          for (int k = 0; k < n_k; ++k)
+            umma_op_pair<kHalf>(tmem_d, adesc + kAdv * k, bdesc + kAdv * k, idesc, (first && k == 0) ? 0u : 1u);
           first = false;
           umma_commit_pair(&empty_bar[stage], 3);
           if (++stage == kPairStages) { stage = 0; phase ^= 1; }
@@ -141,6 +166,7 @@ cl_pair_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constan
     // ===================== epilogue (both CTAs, own 128 TMEM lanes = own 128 output rows) ==========
     const int ew = warp & 3;
     float* tbuf = epi_buf + (warp - 2) * kClEpiBufFloats;
+    const float oscale = (kHalf && p.out_scale) ? p.out_scale[0] : 1.f;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long item = pair_id; item < p.n_items; item += n_pairs) {
       const int mp = static_cast<int>(item % p.n_mp);
@@ -155,13 +181,13 @@ cl_pair_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constan
         float v[16];
         tmem_ld16(taddr + j * 32, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tbuf[lane * 33 + i] = v[i];
+        for (int i = 0; i < 16; ++i) tbuf[lane * 33 + i] = kHalf ? v[i] * oscale : v[i];
         tmem_ld16(taddr + j * 32 + 16, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tbuf[lane * 33 + 16 + i] = v[i];
+        for (int i = 0; i < 16; ++i) tbuf[lane * 33 + 16 + i] = kHalf ? v[i] * oscale : v[i];
         __syncwarp();
         const int tap = h / p.hpt;
-        const int ch = ((h - tap * p.hpt) * 4 + (j & 3)) * 32 + lane;
+        const int ch = (h - tap * p.hpt) * 128 + (j & 3) * 32 + lane;
         if (ch < p.C) {
           float* o = p.out + static_cast<long long>(tap) * p.C + ch;
           for (int r = 0; r < 32; ++r)

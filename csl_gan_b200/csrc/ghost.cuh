@@ -36,6 +36,8 @@ struct GhostParams {
   int slot0, n_slots;        // slots [slot0, slot0 + n_slots)
   int n_items;               // ceil(n_slots / ns)
   float* norm2;              // norm2[slot - slot0] += ||G_slot||^2
+  const float* inv_x;        // FP16 operands: per-slot inverse staging scales (indexed by absolute slot), else NULL
+  const float* inv_y;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
@@ -55,9 +57,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// kHalf: FP16 tiles of 128 rows x 64 channels (the same 128-byte rows, SWIZZLE_128B and 16 KB per tile as the TF32
+// tiles of 32 channels; K = 16 channels per instruction instead of 8)
+template <bool kHalf>
 __global__ void __launch_bounds__(kGThreads, 1)
 ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constant__ CUtensorMap tmap_yt,
                   const __grid_constant__ GhostParams p) {
+  constexpr uint32_t kTileTx = kGTileBytes;
+  constexpr int kCW = kHalf ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kGStages * kGTileBytes);
@@ -81,8 +88,8 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_ob = (p.O + 31) / 32;                // k-blocks of the backprop Gram
-  const int n_cb = (p.C + 31) / 32;
+  const int n_ob = (p.O + kCW - 1) / kCW;          // k-blocks of the backprop Gram
+  const int n_cb = (p.C + kCW - 1) / kCW;
   const int n_taps = p.KH * p.KW;
   const int n_ub = n_taps * n_cb;                  // k-blocks of the activation Gram
 
@@ -93,14 +100,14 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
         const int s0 = p.slot0 + item * p.ns;
         for (int kb = 0; kb < n_ob; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kGTileBytes);
+          mbar_expect_tx(&full_bar[stage], kTileTx);
           tma_load_3d(tiles + stage * kGTileBytes, &tmap_xt, &full_bar[stage], 0, s0 * p.Q, kb);
           if (++stage == kGStages) { stage = 0; phase ^= 1; }
         }
         for (int t = 0; t < n_taps; ++t) {
           for (int cb = 0; cb < n_cb; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], kGTileBytes);
+            mbar_expect_tx(&full_bar[stage], kTileTx);
             tma_load_5d(tiles + stage * kGTileBytes, &tmap_yt, &full_bar[stage], 0, p.tap_woff[t], p.tap_hoff[t], s0,
                         p.tap_plane[t] * n_cb + cb);
             if (++stage == kGStages) { stage = 0; phase ^= 1; }
@@ -110,7 +117,7 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t idesc = kHalf ? umma_idesc_f16(128, 128, 0u) : umma_idesc_tf32(128, 128);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -123,9 +130,9 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
           tc_fence_after();
           const uint64_t desc = umma_desc_k_sw128(smem_u32(tiles + stage * kGTileBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_d, desc + static_cast<uint64_t>(2 * k), desc + static_cast<uint64_t>(2 * k), idesc,
-                      (!first || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)                     // 32 bytes of K per instruction: 8 tf32 / 16 fp16 channels
+            umma_op<kHalf>(tmem_d, desc + static_cast<uint64_t>(2 * k), desc + static_cast<uint64_t>(2 * k), idesc,
+                           (!first || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == kGStages) { stage = 0; phase ^= 1; }
         }
@@ -164,7 +171,13 @@ ghost_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_cons
       const int span = p.Q < 32 ? p.Q : 32;
       for (int o = span >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       const int slot_rel = item * p.ns + sidx;
-      if ((lane % span) == 0 && slot_rel < p.n_slots) atomicAdd(p.norm2 + slot_rel, dot);
+      if ((lane % span) == 0 && slot_rel < p.n_slots) {
+        if (kHalf) {
+          const float sc = p.inv_x[p.slot0 + slot_rel] * p.inv_y[p.slot0 + slot_rel];
+          dot = dot * sc * sc;
+        }
+        atomicAdd(p.norm2 + slot_rel, dot);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

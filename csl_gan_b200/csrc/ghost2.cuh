@@ -54,6 +54,8 @@ struct Ghost2Params {
   int slot0, n_slots;
   int n_items;                 // ceil(n_slots / ns)
   float* norm2;                // norm2[slot - slot0] += ||G_slot||^2
+  const float* inv_x;          // FP16 operands: per-slot inverse staging scales (absolute slot index), else NULL
+  const float* inv_y;
 };
 
 // explicit shared-space accesses with 32-bit addresses: through the lambdas below nvcc loses the address space of
@@ -70,9 +72,12 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiThreads) : "memory"); }
 
+template <bool kHalf>
 __global__ void __launch_bounds__(kG2Threads, 1)
 ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_constant__ CUtensorMap tmap_yt,
                    const __grid_constant__ Ghost2Params p) {
+  constexpr uint32_t kRowB = 128;                           // bytes per chunk row of a tile (32 tf32 / 64 fp16 channels)
+  constexpr int kCW = kHalf ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* Ps = reinterpret_cast<float*>(tiles + kG2Stages * kGTileBytes);
@@ -106,9 +111,9 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_ob = (p.O + 31) / 32;
-  const int n_cb = (p.C + 31) / 32;
-  const uint32_t p_tile_bytes = static_cast<uint32_t>(p.spp * p.npos * 128);
+  const int n_ob = (p.O + kCW - 1) / kCW;
+  const int n_cb = (p.C + kCW - 1) / kCW;
+  const uint32_t p_tile_bytes = static_cast<uint32_t>(p.spp * p.npos) * kRowB;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -117,7 +122,7 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
         const int s0 = p.slot0 + item * p.ns;
         for (int kb = 0; kb < n_ob; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kGTileBytes);
+          mbar_expect_tx(&full_bar[stage], 128 * kRowB);
           tma_load_3d(tiles + stage * kGTileBytes, &tmap_xt, &full_bar[stage], 0, s0 * p.Q, kb);
           if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
         }
@@ -134,7 +139,7 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, 128);
+      const uint32_t idesc = kHalf ? umma_idesc_f16(128, 128, 0u) : umma_idesc_tf32(128, 128);
       int stage = 0; uint32_t phase = 0;
       int bb = 0; uint32_t bb_phase = 0; int pa = 0; uint32_t pa_phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -146,8 +151,8 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
           const uint64_t desc = umma_desc_k_sw128(smem_u32(tiles + stage * kGTileBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(tmem_base + static_cast<uint32_t>(bb * 128), desc + static_cast<uint64_t>(2 * k),
-                      desc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_op<kHalf>(tmem_base + static_cast<uint32_t>(bb * 128), desc + static_cast<uint64_t>(2 * k),
+                           desc + static_cast<uint64_t>(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
         }
@@ -162,8 +167,8 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
             const uint64_t desc = umma_desc_k_sw128(smem_u32(tiles + stage * kGTileBytes));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_tf32(tmem_base + static_cast<uint32_t>(256 + pa * 128), desc + static_cast<uint64_t>(2 * k),
-                        desc + static_cast<uint64_t>(2 * k), idesc, (cb > 0 || k > 0) ? 1u : 0u);
+              umma_op<kHalf>(tmem_base + static_cast<uint32_t>(256 + pa * 128), desc + static_cast<uint64_t>(2 * k),
+                             desc + static_cast<uint64_t>(2 * k), idesc, (cb > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[stage]);
             if (++stage == kG2Stages) { stage = 0; phase ^= 1; }
           }
@@ -320,7 +325,14 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
       }
       epi_bar_sync();
       const int slot_rel = item * p.ns + te;
-      if (te < p.ns && slot_rel < p.n_slots) atomicAdd(p.norm2 + slot_rel, nacc[te]);
+      if (te < p.ns && slot_rel < p.n_slots) {
+        float v = nacc[te];
+        if (kHalf) {
+          const float sc = p.inv_x[p.slot0 + slot_rel] * p.inv_y[p.slot0 + slot_rel];
+          v = v * sc * sc;
+        }
+        atomicAdd(p.norm2 + slot_rel, v);
+      }
       epi_bar_sync();                                               // nacc / BBs are rewritten by the next item
     }
   }

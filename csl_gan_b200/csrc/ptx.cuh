@@ -96,6 +96,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A * B, FP16 inputs (kind::f16; K = 16 per instruction), FP32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kHalf>
+__device__ __forceinline__ void umma_op(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (kHalf) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -132,6 +148,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -156,6 +177,21 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kHalf>
+__device__ __forceinline__ void umma_op_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (kHalf) umma_f16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32_pair(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 // arrive on the barrier at the same shared-memory offset in every CTA of `cta_mask` once all MMAs issued so
 // far by this thread have completed
@@ -193,6 +229,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Instruction descriptor: FP16 x FP16 -> FP32 (kind::f16), dense; a_major / b_major: 0 = K, 1 = MN.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t mn_major) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (mn_major << 15) | (mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // Instruction descriptor: TF32 x TF32 -> FP32, both operands K-major, dense.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4)            // c_format  = F32
@@ -202,6 +243,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
          | (0u << 16)         // b_major   = K
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
+}
+
+// two floats -> packed fp16x2 (round to nearest even), x in the low half
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  return r;
+}
+
+// Power-of-two scale that brings a magnitude `m` into [2^13, 2^14): fp16 keeps 11 significant bits from there
+// down to 2^-14 (28 binades) and 4x headroom to its maximum.  Returns 2^e with e clamped to +-100; m == 0 -> 1.
+__device__ __forceinline__ float half_scale_for(float m) {
+  if (!(m > 0.f) || !isfinite(m)) return 1.0f;
+  int e;
+  frexpf(m, &e);                                            // m = f * 2^e, f in [0.5, 1)
+  int s = 14 - e;
+  s = s > 100 ? 100 : (s < -100 ? -100 : s);
+  return __int_as_float((s + 127) << 23);
 }
 
 __device__ __forceinline__ float round_tf32(float x) {

@@ -54,6 +54,7 @@ class LayerPlan:
         self.Bpad = 0
         self.max_passes = 0
         self.use_ghost = True
+        self.use_half = L.default_operand_dtype() == "f16"   # FP16 operand containers on the channels-last path
         self.gplan = None
         self.force_legacy = False          # tests: exercise the kw-plane (legacy) path on any geometry
         self.impl = None                   # ClLayerPlan when the channels-last path applies
@@ -136,7 +137,8 @@ class LayerPlan:
                     f"{self.name}: Linear layers with >2-D inputs are not supported (got {tuple(act.shape)})")
             g = ClLayerPlan.geometry(self.layer, self.kind, act.shape)
             if not self.force_legacy and L.cl_supported(g[11], g[12]):
-                self.impl = ClLayerPlan(self.name, self.layer, self.kind, self.w_idx, self.b_idx, self.use_ghost)
+                self.impl = ClLayerPlan(self.name, self.layer, self.kind, self.w_idx, self.b_idx, self.use_ghost,
+                                        self.use_half)
                 self.impl.setup(act, Bpad, max_passes)
                 self.Bpad, self.max_passes = Bpad, max_passes
                 self.ready = True

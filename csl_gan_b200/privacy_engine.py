@@ -183,7 +183,8 @@ class PrivacyEngine:
                  auto_clip_and_accum_on_step: bool = True, loss_reduction: str = "mean",
                  split_clip_fake: bool = True, max_passes: int = 2, process_group=None,
                  data_parallel: bool = False, global_batch_size: Optional[int] = None,
-                 per_layer_noise: str = "l2norm", clip_margin: float = 0.0, **misc):
+                 per_layer_noise: str = "l2norm", clip_margin: float = 0.0,
+                 operand_dtype: Optional[str] = None, **misc):
         """`batch_size` is THIS rank's batch.  Under data parallelism the accountant needs the global sampling
         rate: pass `global_batch_size`, or leave it None and the constructor sums the per-rank batch sizes with
         one tiny allreduce.
@@ -194,7 +195,11 @@ class PrivacyEngine:
         fork's choice cannot be verified).
         `clip_margin`: factor = min(1, C*(1 - margin)/(norm + 1e-6)).  The norms and the clipped sum come from
         TF32-rounded tensor-core operands (relative error <= 1e-3), so a clipped per-sample gradient can
-        exceed C by that much; a margin of 2**-9 makes the bound strict.  Default 0 = the reference's formula."""
+        exceed C by that much; a margin of 2**-9 makes the bound strict.  Default 0 = the reference's formula.
+        `operand_dtype`: "f16" (default) stages the tensor-core operands of the channels-last path as FP16 with an
+        exact per-sample power-of-two scale (TF32's 10-bit mantissa, half the bytes, twice the MMA rate); "tf32"
+        keeps fp32 words.  Joint clipping (accum_passes=True) sums two passes in one accumulator and therefore
+        always uses TF32 (the passes' staging scales differ)."""
         if loss_reduction not in ("mean", "sum"):
             raise ValueError("loss_reduction must be 'mean' or 'sum'")
         if per_layer_noise not in ("l2norm", "own"):
@@ -207,6 +212,11 @@ class PrivacyEngine:
         self.sample_size = sample_size
         self.per_layer_noise = per_layer_noise
         self.clip_margin = float(clip_margin)
+        self.operand_dtype = operand_dtype or L.default_operand_dtype()
+        if self.operand_dtype not in ("f16", "tf32"):
+            raise ValueError("operand_dtype must be 'f16' or 'tf32'")
+        if accum_passes:
+            self.operand_dtype = "tf32"
         self.alphas = list(alphas)
         self.noise_multiplier = float(noise_multiplier)
         self.accum_passes = accum_passes
@@ -251,6 +261,7 @@ class PrivacyEngine:
                 w = pidx[id(layer.weight)]
                 b = pidx[id(layer.bias)] if getattr(layer, "bias", None) is not None and layer.bias.requires_grad else None
                 self._plans.append(LayerPlan(name, layer, w, b))
+                self._plans[-1].use_half = self.operand_dtype == "f16"
                 covered.update(id(p) for p in own)
         missing = [n for n, p in zip(self._param_names, self._params) if id(p) not in covered]
         if missing:
@@ -734,16 +745,18 @@ class PrivacyEngine:
             else:
                 ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], 0) for ps in live]
             frow_w = self._factors[plan.w_idx if self._per_layer else 0]
-            for lo, hi, shift in ranges:
-                # scale up to the next 32-slot boundary (Bpad is a multiple of 32, dead slots have factor 0):
-                # the contraction reads whole 32-row K blocks, which may reach past `hi` when Q < 32
-                plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
+            # scale up to the next 32-slot boundary (Bpad is a multiple of 32, dead slots have factor 0):
+            # the contraction reads whole 32-row K blocks, which may reach past `hi` when Q < 32
             if joint or len(ranges) == 1:
+                for lo, hi, shift in ranges:
+                    plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
                 plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False,
                                   factor_row=frow_w)
             else:
-                for i, (lo, hi, _) in enumerate(ranges):
+                # range by range: with FP16 operands every scale_backprops() call has its own common scale
+                for i, (lo, hi, shift) in enumerate(ranges):
+                    plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
                     plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0, factor_row=frow_w)
             if plan.b_idx is not None:
                 frow_b = self._factors[plan.b_idx if self._per_layer else 0]

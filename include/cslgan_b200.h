@@ -168,6 +168,8 @@ typedef struct cg_ghost_plan {
                                 inputs such as the 3-channel image; taps then run over kh only        */
   int Cs;                    /* staged channels per tap: C, or KW*C when merged                       */
   int n_taps;                /* KH*KW, or KH when merged                                              */
+  int cw;                    /* channels per 128-byte chunk row: 32 (TF32 words) or 64 (FP16); Cp and
+                                slot_stride are in these units                                        */
 } cg_ghost_plan;
 typedef cg_ghost_plan cg_cl_plan;
 
@@ -181,6 +183,8 @@ typedef struct cg_ghost_desc {
   int slot0, n_slots;                                       /* slots to process            */
   float* norm2;                                             /* norm2[slot - slot0] +=      */
   int max_ctas;
+  int half;                                                 /* 1: Xt / Yt hold FP16 (cg_stage_*_h), see below */
+  const float* inv_x; const float* inv_y;                   /* half: per-slot inverse staging scales [n_slots_total] */
 } cg_ghost_desc;
 
 /* Two kernels behind one entry point.  When a stride-residue plane has at most 128 positions (Hs*Ws <= 128: the
@@ -202,7 +206,8 @@ int cg_ghost_norm(const cg_ghost_desc* d, const cg_unfold_geom* g, const cg_ghos
  * Linear layers are Q = 1.  CG_EPI_ACCUM writes the gradient-natural layout out[m][tap][c'] (which
  * is the memory order of a channels_last weight).
  * ------------------------------------------------------------------------------------------- */
-int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan);
+int cg_plan_cl(const cg_unfold_geom* g, int merged, cg_cl_plan* plan);              /* TF32: 32-channel chunks */
+int cg_plan_cl_cw(const cg_unfold_geom* g, int merged, int cw, cg_cl_plan* plan);   /* cw = 32 (TF32) / 64 (FP16) */
 
 /* src addressed as src[n*sn + m*sm + oh*sh + ow*sw] (any layout; fastest when sm == 1).
  * Xt[m/32][(slot0+n)*Q + q][m%32] = tf32(scale*src), rows_total = rows of each chunk (n_slots_total*Q);
@@ -216,6 +221,33 @@ int cg_stage_xt(const float* src, long long sn, long long sm, long long sh, long
 int cg_stage_yt(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
                 const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, float* dst, int n_slots_total,
                 int slot0, cg_stream_t stream);
+
+/* FP16 operand containers (the default of the engine's channels-last path).  Same layouts with 2-byte elements
+ * (64-byte chunk rows).  FP16 carries TF32's 10 explicit mantissa bits; its narrow exponent is handled by an EXACT
+ * power-of-two scale per (slot, operand): staged = fp16(scale*src * 2^e), e chosen so that the sample's largest
+ * magnitude lands in [2^13, 2^14); inv[slot0+n] receives 2^-e.  Everything downstream undoes it exactly:
+ *   per-sample results (norms, stored gradients) are multiplied by inv_x[slot]*inv_y[slot] in the epilogue;
+ *   the clipped sum folds factor[slot]*inv_x[slot]*inv_y[slot] / 2^E into the scaled operand (cg_clip_mult,
+ *   cg_scale_slots_h) and multiplies the accumulated tile by 2^E (cg_cl_desc.out_scale).
+ * amax: scratch [n_slots_total] words (zeroed and filled with the per-sample maxima by these calls). */
+int cg_stage_xt_h(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M,
+                  int Ho, int Wo, float scale, void* dst_half, long long rows_total, int slot0, float* bias_rows,
+                  float* sumsq, unsigned int* amax, float* inv, cg_stream_t stream);
+int cg_stage_yt_h(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
+                  const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, void* dst_half, int n_slots_total,
+                  int slot0, unsigned int* amax, float* inv, cg_stream_t stream);
+/* mult[s] = factor[s] * inv_x[s] * inv_y[s] / 2^E for s in [slot_lo, slot_hi), out_scale[0] = 2^E with 2^E the
+ * smallest power of two above max_s factor*inv_x*inv_y (so mult <= 1 and the scaled operand stays in FP16 range;
+ * samples far below the largest contribution lose low bits they could not contribute to the sum anyway).
+ * out_scale points at TWO floats: [0] receives 2^E, [1] is scratch (the raw maximum of the multi-block path). */
+int cg_clip_mult(const float* factor, const float* inv_x, const float* inv_y, int slot_lo, int slot_hi,
+                 float* mult, float* out_scale, cg_stream_t stream);
+/* dst[r][slot*stride + q] = fp16(src * mult[slot]) over FP16 rows (the factor-scaled operand of the clipped sum) */
+int cg_scale_slots_h(const void* src_half, void* dst_half, int rows, long long pitch, long long slot_stride,
+                     int slot_lo, int slot_hi, const float* mult, cg_stream_t stream);
+/* cg_outer_rows_cl over FP16 operands: out = Xt*Yt * inv_x[slot]*inv_y[slot] */
+int cg_outer_rows_cl_h(const void* Xt_half, long long x_rows, const void* Yt_half, long long y_rows, int M, int P,
+                       int slot0, int B, const float* inv_x, const float* inv_y, float* out, cg_stream_t stream);
 
 typedef struct cg_cl_desc {
   const float* Xt; long long xt_pitch; long long xt_rows; int M;   /* xt_rows = n_slots_total*Q (xt_pitch unused) */
@@ -233,7 +265,16 @@ typedef struct cg_cl_desc {
   int pair;                    /* 1: run on CTA pairs (cluster of 2, tcgen05 cta_group::2, 256x256 tiles, each CTA
                                   loads half of the unfolded operand).  Only CG_GROUP_SPLITK + CG_EPI_ACCUM with
                                   M % 256 == 0 and 128-channel multiples (cg_cl_pair_ok); an error otherwise */
+  int half;                    /* 1: Xt / Yt hold FP16 staged by cg_stage_xt_h / cg_stage_yt_h (tcgen05 kind::f16) */
+  const float* inv_x;          /* half, CG_GROUP_SAMPLE: per-slot inverse staging scales [n_slots_total]; the     */
+  const float* inv_y;          /*   epilogues multiply every per-sample result by inv_x[slot] * inv_y[slot]        */
+  const float* out_scale;      /* half, CG_GROUP_SPLITK: device scalar multiplied into the accumulated tile
+                                  (cg_clip_mult) */
 } cg_cl_desc;
+
+/* contraction rows per k-block (32, or 64 for FP16 operands where the window grid allows) and slots per k-block
+ * (1 unless Ho*Wo < kb_rows) of the split-K clipped sum: what the host needs to pick a split-K group count */
+int cg_cl_kblock_rows(const cg_unfold_geom* g, int half, int* kb_rows, int* kb_s);
 
 /* 1 when cg_cl_contract accepts d->pair = 1 for this layer (split-K clipped sum), else 0 */
 int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan);

@@ -102,10 +102,11 @@ def _conv_case(B, Cin, Cout, H, W, k, s, p, d=1, seed=0):
     (2, 4, 6, 13, 12, 3, 2, 0, 2),       # dilation 2, no padding
     (2, 3, 5, 10, 10, 4, 3, 1, 1),       # stride 3, even kernel
 ])
-@pytest.mark.parametrize("path", ["channels_last", "channels_last_from_cl_tensors", "kw_planes"])
+@pytest.mark.parametrize("path", ["channels_last", "channels_last_from_cl_tensors", "kw_planes", "channels_last_tf32"])
 def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d, path):
     """staging + contraction (all three epilogues) vs the oracle's unfold/einsum, on both operand paths:
-    channels-last MN-major (main) and kw-plane K-major (geometries the main path cannot tile)."""
+    channels-last MN-major (main; FP16 operand containers by default, TF32 words in the *_tf32 variant) and kw-plane
+    K-major (geometries the main path cannot tile)."""
     from csl_gan_b200.grad_sample import LayerPlan
     conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p, d)
     if path != "kw_planes" and not L.cl_supported(Ho, Wo):
@@ -115,6 +116,8 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d,
     plan = LayerPlan("conv", conv, 0, 1)
     plan.force_legacy = path == "kw_planes"
     plan.use_ghost = False
+    plan.use_half = path != "channels_last_tf32"
+    path = "channels_last" if path == "channels_last_tf32" else path
     Bpad = 32
     Ag, Bg = A.to(DEV), Bp.to(DEV)
     if path == "channels_last_from_cl_tensors":
@@ -152,7 +155,8 @@ def test_conv_per_sample_grads_store_sumsq_accum(B, Cin, Cout, H, W, k, s, p, d,
     (70, 256, 512, 8, 8, 3, 1, 1),       # Q = 64, 3x3 stride 1: 18 half tiles, two 256-row pairs
     (33, 384, 256, 4, 4, 5, 2, 2),       # Q = 4: 8 samples per k-block, ragged last k-block, 3 half tiles per tap
 ])
-def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, W, k, s, p):
+@pytest.mark.parametrize("operands", ["f16", "tf32"])
+def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, W, k, s, p, operands):
     """cl_pair_kernel (cluster of 2, tcgen05 cta_group::2) vs cl_contract_kernel vs the oracle, split-K over
     several groups so the pipeline wraps and both accumulator stages are used."""
     from csl_gan_b200.grad_sample import LayerPlan
@@ -160,6 +164,7 @@ def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, 
     gw_ref, _ = O.conv2d_grad_sample(conv, A, Bp)
     conv = conv.to(DEV)
     plan = LayerPlan("conv", conv, 0, 1)
+    plan.use_half = operands == "f16"
     Bpad = (B + 31) // 32 * 32
     plan.capture_activation(A.to(DEV).contiguous(memory_format=torch.channels_last), 0, Bpad, 1)
     plan.capture_backprop(Bp.to(DEV).contiguous(memory_format=torch.channels_last), 0, 1.0)
@@ -177,7 +182,7 @@ def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, 
             torch.cuda.synchronize()
             outs[(pair, sms)] = out.cpu()
             assert ((out.cpu() - ref).norm() / ref.norm()).item() < 1e-3, (pair, sms)
-    # same TF32 products, different summation order only
+    # same products, different summation order only
     assert ((outs[(True, 148)] - outs[(False, 148)]).norm() / ref.norm()).item() < 1e-5
 
 
@@ -188,7 +193,8 @@ def test_cta_pair_clipped_sum_matches_single_cta_and_reference(B, Cin, Cout, H, 
     (4, 8, 8, 4, 4, 3, 1, 1),            # stride 1, Q = 16
     (2, 16, 24, 16, 32, 3, 2, 1),        # Q = 128, one sample per tile, non-square
 ])
-def test_ghost_norms_match_direct_and_oracle(B, Cin, Cout, H, W, k, s, p):
+@pytest.mark.parametrize("operands", ["f16", "tf32"])
+def test_ghost_norms_match_direct_and_oracle(B, Cin, Cout, H, W, k, s, p, operands):
     from csl_gan_b200.grad_sample import LayerPlan
     conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p)
     gw_ref, _ = O.conv2d_grad_sample(conv, A, Bp)
@@ -198,6 +204,7 @@ def test_ghost_norms_match_direct_and_oracle(B, Cin, Cout, H, W, k, s, p):
     for ghost in (True, False):
         plan = LayerPlan("conv", conv, 0, 1)
         plan.use_ghost = ghost
+        plan.use_half = operands == "f16"
         plan.capture_activation(A.to(DEV), 1, 32, 2)          # second pass: exercises slot offsets
         plan.capture_backprop(Bp.to(DEV), 1, 1.0)
         assert plan.path == "channels_last" and plan.impl.ghost == ghost
@@ -392,3 +399,64 @@ def test_errors_are_loud():
     d.KH = 99
     with pytest.raises(L.CslGanCudaError):
         L.call("cg_contract", C.byref(d), st())
+
+
+@pytest.mark.parametrize("layer", ["conv_q256", "conv_q16_pair", "linear"])
+def test_fp16_operands_survive_a_wide_dynamic_range(layer):
+    """Adversarial case for the FP16 operand containers: per-sample magnitudes spread over 2^+-25 in
+    BOTH operands (far outside FP16's 2^-24 .. 2^16; the per-sample gradient norms then span 2^+-50, about what fp32
+    itself can square), plus 2^20 of spread inside every sample.  The exact per-sample
+    power-of-two scales keep per-sample norms within 1e-3 of the fp64 reference for EVERY sample, and the clipped sum
+    within 1e-3 normwise (with clipping active the factors equalise the samples, so small ones matter)."""
+    from csl_gan_b200.grad_sample import LayerPlan
+    g = torch.Generator().manual_seed(11)
+    B, Bpad = 24, 32
+    if layer == "linear":
+        mod = torch.nn.Linear(200, 64, bias=False)
+        A = torch.randn(B, 200, generator=g)
+        Bp = torch.randn(B, 64, generator=g)
+    else:
+        Cin, Cout, H = (64, 128, 32) if layer == "conv_q256" else (128, 256, 8)
+        mod = torch.nn.Conv2d(Cin, Cout, 5, stride=2, padding=2, bias=False)
+        A = torch.randn(B, Cin, H, H, generator=g)
+        Bp = torch.randn(B, Cout, H // 2, H // 2, generator=g)
+    # spread inside a sample: a log-uniform envelope over 2^-20 .. 1 per element
+    A = A * torch.exp2(-20 * torch.rand(A.shape, generator=g))
+    Bp = Bp * torch.exp2(-20 * torch.rand(Bp.shape, generator=g))
+    # spread across samples: 2^-25 .. 2^25, independently for the two operands
+    ea = torch.randint(-25, 26, (B,), generator=g).float()
+    eb = torch.randint(-25, 26, (B,), generator=g).float()
+    ea[0], eb[0], ea[1], eb[1] = 25, 25, -25, -25
+    A = A * torch.exp2(ea).view(B, *([1] * (A.dim() - 1)))
+    Bp = Bp * torch.exp2(eb).view(B, *([1] * (Bp.dim() - 1)))
+    if layer == "linear":
+        gw_ref = torch.einsum("ni,nj->nij", Bp.double(), A.double())
+    else:
+        U = F.unfold(A.double(), 5, padding=2, stride=2)
+        gw_ref = torch.einsum("noq,npq->nop", Bp.double().reshape(B, Bp.shape[1], -1), U).reshape(B, *mod.weight.shape)
+    n_ref = gw_ref.reshape(B, -1).norm(dim=1)
+    mod = mod.to(DEV)
+    plan = LayerPlan(layer, mod, 0, None)
+    plan.use_half = True
+    plan.use_ghost = layer == "conv_q16_pair"
+    plan.capture_activation(A.to(DEV), 0, Bpad, 1)
+    plan.capture_backprop(Bp.to(DEV), 0, 1.0)
+    assert plan.impl is not None and plan.impl.half
+    norm2 = torch.zeros(Bpad, device=DEV)
+    plan.weight_norm2(norm2, 0, B)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(norm2[:B].sqrt().cpu().double().numpy(), n_ref.numpy(), rtol=1e-3)
+    # clipping active: C = the median norm, so samples 2^100 apart end up with comparable weight in the sum
+    Cthr = n_ref.median().item()
+    f = torch.zeros(Bpad, device=DEV)
+    f[:B] = (Cthr / (n_ref + 1e-6)).clamp(max=1.0).float().to(DEV)
+    plan.scale_backprops(f, 0, Bpad)
+    out = torch.empty_like(mod.weight)
+    plan.weighted_sum(out, 0, B, 148, accumulate=False, factor_row=f)
+    torch.cuda.synchronize()
+    ref = torch.einsum("n,n...->...", f[:B].cpu().double(), gw_ref)
+    assert ((out.cpu().double() - ref).norm() / ref.norm()).item() < 1e-3
+    # materialised per-sample gradients carry the exact scales back too
+    gs = plan.materialize(0, B).cpu().double()
+    for n in range(B):
+        assert ((gs[n] - gw_ref[n]).norm() / gw_ref[n].norm()).item() < 1e-3, n
