@@ -273,7 +273,7 @@ def plan_ghost(geom: UnfoldGeom):
 def plan_cl(geom: UnfoldGeom, merged: bool, cw: int = 32) -> GhostPlan:
     """Staging plan of the channels-last path; cw = channels per 128-byte chunk row (32 TF32 words / 64 FP16)."""
     p = GhostPlan()
-    call("cg_plan_cl_cw", C.byref(geom), 1 if merged else 0, cw, C.byref(p))
+    call("cg_plan_cl_cw", C.byref(geom), int(merged), cw, C.byref(p))      # merged: 0 / 1 (kw) / 2 (kh and kw)
     return p
 
 

@@ -87,13 +87,13 @@ class ClLayerPlan:
         merged = self.kind != "linear" and Cn < MERGE_BELOW and kw > 1 and not ghost_ok
         # FP16 operand containers (kind::f16: 16 contraction rows per instruction) wherever a per-sample k-block is a
         # multiple of 16 rows; TF32 words otherwise (per-sample groups of 8 | Q < 16 positions)
-        # (thin inputs -- merged filter columns, e.g. 3 x 5 = 15 staged channels -- keep 32-channel TF32 chunks: a
-        # 64-channel chunk would be 77 % padding and split the 5 taps over two tiles)
-        self.half = bool(self.use_half and not merged
-                         and (self.kind == "linear" or self.Q >= 32 or self.Q % 16 == 0))
+        self.half = bool(self.use_half and (self.kind == "linear" or self.Q >= 32 or self.Q % 16 == 0))
         dt = torch.float16 if self.half else torch.float32
         cw = self.cw = 64 if self.half else 32            # channels per 128-byte chunk row
-        self.plan = L.plan_cl(self.geom, merged, cw)
+        # thin inputs: TF32 folds the filter COLUMNS into the channels (3 x 5 = 15 of 32, five taps over kh); with
+        # FP16's 64-channel chunks the whole window is folded (3 x 5 x 5 = 75 of 128: plain im2col rows, one tap,
+        # one TMA box per k-block) -- the staged bytes are the same, the contraction is a single tile
+        self.plan = L.plan_cl(self.geom, (2 if self.half else 1) if merged else 0, cw)
         self.n_planes = self.plan.n_rh * self.plan.n_rw
         self.kblock = L.cl_kblock_rows(self.geom, self.half)      # (rows, slots) per k-block of the clipped sum
         # chunk-major staging: Xt[m/cw][slot*Q + q][cw], Yt[plane*n_cb + c/cw][slot][hs][ws][cw]
@@ -306,6 +306,7 @@ class ClLayerPlan:
         else:
             n_groups = _pick_split_k(n_tiles, units, sm_count)
         d.pair = 1 if self.pair else 0
+        d.max_ctas = sm_count                              # (the engine passes fewer SMs while an allreduce is in flight)
         if self.half:
             d.out_scale = L.ptr(self.out_scale)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SPLITK, n_groups, slot_lo, slot_hi

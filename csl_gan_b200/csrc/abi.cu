@@ -312,9 +312,19 @@ int stage_xt_t(const float* src, long long sn, long long sm, long long sh, long 
     // Linear layers: rows [B][M]; one warp per row does the maximum, the scale, the sums and the staging
     if (static_cast<long long>(slot0 + B) > rows_total) return fail("Xt too small for slots [%d, %d)", slot0, slot0 + B);
     if (sizeof(T) == 2 && !inv) return fail("FP16 staging needs the inverse-scale output");
-    const long long blocks = (static_cast<long long>(B) + 7) / 8;
-    cg::stage_rows_cl_kernel<T><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(src, sn, B, M, scale, dst, rows_total,
-                                                                                      slot0, bias_rows, sumsq, inv);
+    // threads per row: one (tiny rows), a warp, or a whole block (wide rows, few of them)
+    if (M <= 16) {
+      const long long blocks = (static_cast<long long>(B) + 255) / 256;
+      cg::stage_rows_cl_kernel<T, 1><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(src, sn, B, M, scale, dst,
+                                                                                            rows_total, slot0, bias_rows, sumsq, inv);
+    } else if (M >= 2048) {
+      cg::stage_rows_cl_kernel<T, 256><<<static_cast<unsigned>(B), 256, 0, S(stream)>>>(src, sn, B, M, scale, dst,
+                                                                                         rows_total, slot0, bias_rows, sumsq, inv);
+    } else {
+      const long long blocks = (static_cast<long long>(B) + 7) / 8;
+      cg::stage_rows_cl_kernel<T, 32><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(src, sn, B, M, scale, dst,
+                                                                                             rows_total, slot0, bias_rows, sumsq, inv);
+    }
     CG_LAUNCH_CHECK();
     return 0;
   }
@@ -391,6 +401,7 @@ int stage_yt_t(const float* src, long long sn, long long sc, long long sh, long 
   p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;
   p.sn = sn; p.sc = sc; p.sh_ = sh; p.sw_ = sw;
   p.Cs = plan->Cs; p.n_cb = n_cb; p.merged = plan->merged; p.KW = g->KW; p.dw = g->dw; p.pw = g->pw;
+  p.dh = g->dh; p.ph = g->ph;
   p.Hs = plan->Hs; p.Ws = plan->Ws; p.n_rh = plan->n_rh; p.n_rw = plan->n_rw; p.sth = g->sh; p.stw = g->sw;
   p.ah_min = plan->ah_min; p.aw_min = plan->aw_min;
   for (int i = 0; i < CG_MAX_KH; ++i) { p.rho_h[i] = plan->rho_h[i]; p.rho_w[i] = plan->rho_w[i]; }
@@ -398,7 +409,7 @@ int stage_yt_t(const float* src, long long sn, long long sc, long long sh, long 
   p.slot_stride = plan->slot_stride;
   p.chunk_stride = plan->slot_stride * n_slots_total;
   const int n_pos = plan->Hs * plan->Ws;
-  const long long extent = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1) * sh +
+  const long long extent = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1 + g->KH * g->dh) * sh +
                            static_cast<long long>(g->W - 1 + g->KW * g->dw) * sw;
   if (sc < 0 || sh < 0 || sw < 0 || extent >= (1LL << 31) || plan->slot_stride >= (1LL << 31))
     return fail("cg_stage_yt: one sample must span fewer than 2^31 elements with non-negative strides");
@@ -703,8 +714,16 @@ int cg_plan_cl_cw(const cg_unfold_geom* g, int merged, int cw, cg_cl_plan* plan)
   axis_plan(g->KH, g->sh, g->dh, g->ph, ah, jh, plan->rho_h, &plan->n_rh, &ah_min, &ah_max);
   plan->ah_min = ah_min;
   plan->Hs = g->Ho + ah_max - ah_min;
-  plan->merged = merged ? 1 : 0;
-  if (merged) {
+  plan->merged = merged == 2 ? 2 : (merged ? 1 : 0);
+  if (merged == 2) {
+    // the whole filter window lives in the channel axis (c' = (kh*KW + kw)*C + c): plain im2col rows, ONE tap, one
+    // TMA box per k-block; used for thin inputs with FP16 operands (3 x 5 x 5 = 75 staged channels in 2 chunks of 64)
+    plan->n_rh = 1; plan->rho_h[0] = 0; plan->ah_min = 0; plan->Hs = g->Ho;
+    plan->n_rw = 1; plan->rho_w[0] = 0; plan->aw_min = 0; plan->Ws = g->Wo;
+    plan->Cs = g->KH * g->KW * g->C;
+    plan->n_taps = 1;
+    plan->tap_plane[0] = 0; plan->tap_hoff[0] = 0; plan->tap_woff[0] = 0;
+  } else if (merged) {
     // filter columns live in the channel axis: one plane per row residue, window rows of exactly Wo
     plan->n_rw = 1; plan->rho_w[0] = 0; plan->aw_min = 0;
     plan->Ws = g->Wo;

@@ -377,7 +377,8 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
                 const int ch = cb * Cfg::kCW + h * 16 + i;
                 if (ch < p.C) {
                   int kh, kw, cc;
-                  if (p.merged) { kh = tap; kw = ch / p.Corig; cc = ch - kw * p.Corig; }
+                  if (p.merged == 2) { const int t = ch / p.Corig; cc = ch - t * p.Corig; kh = t / p.KW; kw = t - kh * p.KW; }
+                  else if (p.merged) { kh = tap; kw = ch / p.Corig; cc = ch - kw * p.Corig; }
                   else { kh = tap / p.KW; kw = tap - kh * p.KW; cc = ch; }
                   obase[static_cast<long long>(cc) * khkw + kh * p.KW + kw] = kHalf ? v[i] * gscale : v[i];
                 }
@@ -646,44 +647,77 @@ __global__ void stage_xt_vec2_kernel(const float* __restrict__ src, long long sn
   }
 }
 
-// Q = 1 sources with contiguous rows (Linear layers: [B][M] activations / backprops): ONE WARP PER ROW, several rows
-// per block, coalesced 8-byte (or 4-byte) loads, warp-shuffle reductions for the row maximum (FP16 scale) and the
-// sum of squares, and the per-sample bias gradient -- which for Q = 1 is the scaled row itself -- stored directly:
-// no atomics, no memsets, no separate absmax pass (the second sweep over the row hits L1/L2).
-template <typename T>
+// Q = 1 sources with contiguous rows (Linear layers: [B][M] activations / backprops): kTPR threads per row -- one
+// thread (M <= 16), one warp, or a whole block (M >= 2048) -- coalesced 16 / 8 / 4-byte loads, shuffle reductions
+// for the row maximum (FP16 scale) and the sum of squares, and the per-sample bias gradient -- which for Q = 1 is the
+// scaled row itself -- stored directly: no atomics, no memsets, no separate absmax pass (the second sweep over the
+// row hits L1/L2).
+template <typename T, int kTPR>
 __global__ void __launch_bounds__(256)
 stage_rows_cl_kernel(const float* __restrict__ src, long long sn, int B, int M, float scale, T* __restrict__ dst,
                      long long rows_total, int slot0, float* __restrict__ bias_rows, float* __restrict__ sumsq,
                      float* __restrict__ inv) {
-  const int n = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= B) return;
+  __shared__ float sh_red[8];
+  const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = static_cast<int>(gtid / kTPR);
+  const int lane = static_cast<int>(gtid - static_cast<long long>(n) * kTPR);      // position inside the row's team
+  if (kTPR < 256 && n >= B) return;                 // (block-per-row: every thread of the block has the same n < B)
   const float* s = src + static_cast<long long>(n) * sn;
   const int slot = slot0 + n;
-  const bool v2 = (M & 1) == 0 && (reinterpret_cast<uintptr_t>(s) & 7) == 0;
+  constexpr int CW = 128 / sizeof(T);
+  // vector width of the sweeps: 4 floats when rows are 16-byte aligned, 2 when 8-byte aligned, else 1
+  const int vw = kTPR == 1 ? 1
+               : ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) ? 4
+               : ((M & 1) == 0 && (reinterpret_cast<uintptr_t>(s) & 7) == 0) ? 2 : 1;
+  auto team_reduce = [&](float v, bool is_max) -> float {
+    if (kTPR == 1) return v;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    if (kTPR == 32) return v;
+    __syncthreads();                                // sh_red reuse
+    if ((threadIdx.x & 31) == 0) sh_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sh_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, sh_red[i]) : r + sh_red[i];
+    return r;
+  };
   float hsc = 1.f;
   if (sizeof(T) == 2) {
     float mx = 0.f;
-    if (v2) {
-      for (int m = 2 * lane; m < M; m += 64) {
+    if (vw == 4) {
+      for (int m = 4 * lane; m < M; m += 4 * kTPR) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s + m));
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+    } else if (vw == 2) {
+      for (int m = 2 * lane; m < M; m += 2 * kTPR) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(s + m));
         mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
       }
     } else {
-      for (int m = lane; m < M; m += 32) mx = fmaxf(mx, fabsf(__ldg(s + m)));
+      for (int m = lane; m < M; m += kTPR) mx = fmaxf(mx, fabsf(__ldg(s + m)));
     }
-    mx = warp_max(mx);
+    mx = team_reduce(mx, true);
     hsc = half_scale_for(fabsf(scale) * mx);
     if (lane == 0) inv[slot] = 1.0f / hsc;
   }
-  constexpr int CW = 128 / sizeof(T);
   T* d = dst + static_cast<long long>(slot) * CW;
   const long long chunk = rows_total * CW;
   float* brow = bias_rows ? bias_rows + static_cast<long long>(slot) * M : nullptr;
-  const bool b2 = brow && (reinterpret_cast<uintptr_t>(brow) & 7) == 0;
   float ssq = 0.f;
-  if (v2) {
-    for (int m = 2 * lane; m < M; m += 64) {
+  if (vw == 4) {
+    const bool b4 = brow && (reinterpret_cast<uintptr_t>(brow) & 15) == 0;
+    for (int m = 4 * lane; m < M; m += 4 * kTPR) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(s + m));
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
+      if (b4) *reinterpret_cast<float4*>(brow + m) = v;
+      else if (brow) { brow[m] = v.x; brow[m + 1] = v.y; brow[m + 2] = v.z; brow[m + 3] = v.w; }
+      st_elem4(d + static_cast<long long>(m / CW) * chunk + (m % CW), v, hsc);
+    }
+  } else if (vw == 2) {
+    const bool b2 = brow && (reinterpret_cast<uintptr_t>(brow) & 7) == 0;
+    for (int m = 2 * lane; m < M; m += 2 * kTPR) {
       float2 v = __ldg(reinterpret_cast<const float2*>(s + m));
       v.x *= scale; v.y *= scale;
       ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, ssq));
@@ -692,16 +726,16 @@ stage_rows_cl_kernel(const float* __restrict__ src, long long sn, int B, int M, 
       st_elem2(d + static_cast<long long>(m / CW) * chunk + (m % CW), v, hsc);
     }
   } else {
-    for (int m = lane; m < M; m += 32) {
+    for (int m = lane; m < M; m += kTPR) {
       const float v = scale * __ldg(s + m);
       ssq = fmaf(v, v, ssq);
       if (brow) brow[m] = v;
       st_elem(d + static_cast<long long>(m / CW) * chunk + (m % CW), v, hsc);
     }
   }
-  // the chunk-row tail [M, round_up(M, 32)) reads as zero: written once at allocation, never touched
+  // the chunk-row tail [M, round_up(M, CW)) reads as zero: written once at allocation, never touched
   if (sumsq) {
-    ssq = warp_sum(ssq);
+    ssq = team_reduce(ssq, false);
     if (lane == 0) sumsq[slot] = ssq;
   }
 }
@@ -789,7 +823,8 @@ struct YtParams {
   int B, C, H, W;              // source [B][C][H][W] through strides
   long long sn, sc, sh_, sw_;
   int Cs, n_cb;                // staged channels (merged: KW*C) and 128-byte chunks
-  int merged, KW, dw, pw;      // merged-kw: channel = kw*C + c, column = ow*sw - pw + kw*dw
+  int merged, KW, dw, pw;      // merged-kw (1): channel = kw*C + c, column = ow*sw - pw + kw*dw
+  int dh, ph;                  // merged-all (2): channel = (kh*KW + kw)*C + c, row = oh*sh - ph + kh*dh as well
   int Hs, Ws, n_rh, n_rw, sth, stw, ah_min, aw_min;
   int rho_h[CG_MAX_KH], rho_w[CG_MAX_KH];
   float scale;
@@ -823,15 +858,20 @@ stage_yt_kernel(const float* __restrict__ src, const __grid_constant__ YtParams 
   const int sh = static_cast<int>(p.sh_), sw = static_cast<int>(p.sw_), sc = static_cast<int>(p.sc);
   const int H = p.H, W = p.W, Ws = p.Ws, sth = p.sth, stw = p.stw;
   const float scale = p.scale;
-  int off[4], wk[4];
+  int off[4], wk[4], hk[4];
   bool ok[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int cs = chi * CW + 4 * l8 + j;
-    int c = cs; wk[j] = 0;
-    if (p.merged) { const int kw = cs / p.C; c = cs - kw * p.C; wk[j] = kw * p.dw - p.pw; }
+    int c = cs; wk[j] = 0; hk[j] = 0;
+    if (p.merged == 1) { const int kw = cs / p.C; c = cs - kw * p.C; wk[j] = kw * p.dw - p.pw; }
+    else if (p.merged == 2) {
+      const int t = cs / p.C; c = cs - t * p.C;
+      const int kh = t / p.KW, kw = t - kh * p.KW;
+      wk[j] = kw * p.dw - p.pw; hk[j] = kh * p.dh - p.ph;
+    }
     ok[j] = cs < p.Cs;
-    off[j] = ok[j] ? c * sc + wk[j] * sw : 0;
+    off[j] = ok[j] ? c * sc + wk[j] * sw + hk[j] * sh : 0;
   }
   const float* s[kYtSamples];
   T* d[kYtSamples];
@@ -867,7 +907,10 @@ stage_yt_kernel(const float* __restrict__ src, const __grid_constant__ YtParams 
     } else {
       bool in[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const int w = w0 + wk[j]; in[j] = ok[j] && h_ok && w >= 0 && w < W; }
+      for (int j = 0; j < 4; ++j) {
+        const int w = w0 + wk[j], hj = h + hk[j];
+        in[j] = ok[j] && hj >= 0 && hj < H && w >= 0 && w < W;
+      }
 #pragma unroll
       for (int k = 0; k < kYtSamples; ++k) {
         v[k].x = in[0] ? __ldg(s[k] + base + off[0]) : 0.f;

@@ -189,6 +189,9 @@ class DiscriminatorStep:
             if self.collect_stats:
                 with torch.no_grad():
                     res.stats.update(self._grad_stats())
+            if getattr(eng, "overlap_allreduce", False) and len(opt.penalty) > 0:
+                # the penalty gradient is added to p.summed_grad AFTER accumulate_batch(): the allreduce must see it
+                eng.overlap_allreduce = False
             eng.clip()
             if opt.grad_clip_split:
                 eng.accum_grads_across_passes()

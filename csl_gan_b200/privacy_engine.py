@@ -184,7 +184,8 @@ class PrivacyEngine:
                  split_clip_fake: bool = True, max_passes: int = 2, process_group=None,
                  data_parallel: bool = False, global_batch_size: Optional[int] = None,
                  per_layer_noise: str = "l2norm", clip_margin: float = 0.0,
-                 operand_dtype: Optional[str] = None, **misc):
+                 operand_dtype: Optional[str] = None, overlap_allreduce: bool = False, nccl_reserve_sms: int = 8,
+                 **misc):
         """`batch_size` is THIS rank's batch.  Under data parallelism the accountant needs the global sampling
         rate: pass `global_batch_size`, or leave it None and the constructor sums the per-rank batch sizes with
         one tiny allreduce.
@@ -199,7 +200,13 @@ class PrivacyEngine:
         `operand_dtype`: "f16" (default) stages the tensor-core operands of the channels-last path as FP16 with an
         exact per-sample power-of-two scale (TF32's 10-bit mantissa, half the bytes, twice the MMA rate); "tf32"
         keeps fp32 words.  Joint clipping (accum_passes=True) sums two passes in one accumulator and therefore
-        always uses TF32 (the passes' staging scales differ)."""
+        always uses TF32 (the passes' staging scales differ).
+        `overlap_allreduce` (data parallel): clip() walks the layers from the last to the first and all-reduces
+        every finished bucket of the flat clipped-sum buffer asynchronously (NCCL stream), so the collective of the
+        large late layers runs under the contractions of the early ones; the persistent GEMM kernels launched
+        meanwhile leave `nccl_reserve_sms` SMs to NCCL.  step() only waits.  Because the reduction has then already
+        happened, anything the caller adds to p.summed_grad after accumulate_batch() must be identical on every
+        rank (DiscriminatorStep switches the overlap off for steps that add a penalty gradient)."""
         if loss_reduction not in ("mean", "sum"):
             raise ValueError("loss_reduction must be 'mean' or 'sum'")
         if per_layer_noise not in ("l2norm", "own"):
@@ -217,6 +224,10 @@ class PrivacyEngine:
             raise ValueError("operand_dtype must be 'f16' or 'tf32'")
         if accum_passes:
             self.operand_dtype = "tf32"
+        self.overlap_allreduce = bool(overlap_allreduce)
+        self.nccl_reserve_sms = int(nccl_reserve_sms)
+        self._reduce_works: list = []
+        self._reduced_early = False
         self.alphas = list(alphas)
         self.noise_multiplier = float(noise_multiplier)
         self.accum_passes = accum_passes
@@ -729,7 +740,15 @@ class PrivacyEngine:
             self._clipped = outs
             return outs
         slot_hi = (n_passes - 1) * self.Bpad + self._pass_B[n_passes - 1]
-        for plan in self._plans:
+        plans, buckets = self._plans, None
+        if self.data_parallel and self.overlap_allreduce:
+            buckets = self._reduce_buckets()
+            if buckets is not None:
+                plans = list(reversed(self._plans))          # last layers first: their (large) sums reduce under the rest
+                flat[self._n_theta:].fill_(float(self._cur_B))
+                self._reduced_early = True
+        sms = self._sm_count
+        for plan in plans:
             live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
             if not live:
                 outs[plan.w_idx].zero_()
@@ -751,19 +770,54 @@ class PrivacyEngine:
                 for lo, hi, shift in ranges:
                     plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
-                plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], self._sm_count, accumulate=False,
+                plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], sms, accumulate=False,
                                   factor_row=frow_w)
             else:
                 # range by range: with FP16 operands every scale_backprops() call has its own common scale
                 for i, (lo, hi, shift) in enumerate(ranges):
                     plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
-                    plan.weighted_sum(outs[plan.w_idx], lo, hi, self._sm_count, accumulate=i > 0, factor_row=frow_w)
+                    plan.weighted_sum(outs[plan.w_idx], lo, hi, sms, accumulate=i > 0, factor_row=frow_w)
             if plan.b_idx is not None:
                 frow_b = self._factors[plan.b_idx if self._per_layer else 0]
                 for i, (lo, hi, shift) in enumerate(ranges):
                     plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=i > 0, factor_shift=shift)
+            if buckets is not None and plan in buckets:
+                import torch.distributed as dist
+                a, b = buckets[plan]
+                self._reduce_works.append(dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=self.process_group,
+                                                          async_op=True))
+                sms = max(2, self._sm_count - self.nccl_reserve_sms)    # leave NCCL its SMs from here on
         self._clipped = outs
         return outs
+
+    def _reduce_buckets(self, min_bytes: int = 1 << 21):
+        """{plan: (lo, hi)}: after that plan's sums are written (walking the layers last to first) the slice
+        flat[lo:hi] -- a contiguous run of whole layers, at least `min_bytes` unless it is the last one -- is complete
+        and can be all-reduced.  The live-sample count (last element) rides with the first bucket.  None when a
+        parameter is not a view of the flat buffer or the layers are not laid out in parameter order."""
+        offs, off = [], 0
+        for p in self._params:
+            if not (p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))):
+                return None
+            offs.append(off)
+            off += p.numel()
+        spans = []
+        for plan in self._plans:
+            idx = [plan.w_idx] + ([plan.b_idx] if plan.b_idx is not None else [])
+            lo = min(offs[k] for k in idx)
+            hi = max(offs[k] + self._params[k].numel() for k in idx)
+            if hi - lo != sum(self._params[k].numel() for k in idx):
+                return None
+            spans.append((lo, hi))
+        if any(spans[i][1] != spans[i + 1][0] for i in range(len(spans) - 1)) or spans[0][0] != 0 or spans[-1][1] != off:
+            return None
+        out, hi = {}, off + 1                                  # + the count element
+        for i in range(len(self._plans) - 1, -1, -1):
+            lo = spans[i][0]
+            if (hi - lo) * 4 >= min_bytes or i == 0:
+                out[self._plans[i]] = (lo, hi)
+                hi = lo
+        return out
 
     def accum_grads_across_passes(self):
         """Sum the per-pass clipped sums (reference train.py:402).  Already fused into clip()."""
@@ -780,8 +834,10 @@ class PrivacyEngine:
                 p.summed_grad = c
             self._summed_flat = self._clipped_flat
         elif self._summed_views_intact() and self._clipped_flat is not None:
+            self._wait_reduces()
             self._summed_flat.add_(self._clipped_flat)          # gradient accumulation: one kernel, count included
         else:
+            self._wait_reduces()
             self._summed_flat = None
             for p, c in zip(self._params, self._clipped):
                 if getattr(p, "summed_grad", None) is None:
@@ -794,6 +850,13 @@ class PrivacyEngine:
         self._clipped_flat = None
         self._reset_capture()
         self._drop_grad_sample_attrs()
+
+    def _wait_reduces(self):
+        for w in self._reduce_works:
+            w.wait()
+        had = bool(self._reduce_works)
+        self._reduce_works = []
+        return had
 
     def _summed_views_intact(self) -> bool:
         """Are the p.summed_grad tensors still the views into `_summed_flat` this engine handed out?  (The caller
@@ -843,7 +906,12 @@ class PrivacyEngine:
         bs = float(self._accum_bs)
         div_dev = None
         if self.data_parallel:
-            div_dev = self._allreduce_summed(bs)            # device scalar: the GLOBAL number of samples
+            if self._reduced_early:
+                # clip() already reduced every bucket (overlap_allreduce): only wait; the count rode along
+                self._wait_reduces()
+                div_dev = self._summed_flat[self._n_theta:]
+            else:
+                div_dev = self._allreduce_summed(bs)        # device scalar: the GLOBAL number of samples
         mean = self.loss_reduction == "mean"
         st = L.stream_ptr(self.device)
         od = getattr(self, "_offset_dev", None)
@@ -861,6 +929,7 @@ class PrivacyEngine:
             p.grad = p.summed_grad                           # noised in place
             p.summed_grad = None
         self._summed_flat = None
+        self._reduced_early = False
         if od is not None:
             if inc:
                 L.call("cg_philox_advance", L.ptr(od), inc, st)

@@ -9,12 +9,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _step(D, real, fake, B, dev, data_parallel, seed=77, sigma=2.0, C=1.5):
+def _step(D, real, fake, B, dev, data_parallel, seed=77, sigma=2.0, C=1.5, overlap=False):
     import csl_gan_b200 as cg
     D = copy.deepcopy(D).to(dev)
     opt = torch.optim.SGD(D.parameters(), lr=0.0)
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=60000, noise_multiplier=sigma, max_grad_norm=C,
-                           num_private_passes=1, auto_clip_and_accum_on_step=False, data_parallel=data_parallel)
+                           num_private_passes=1, auto_clip_and_accum_on_step=False, data_parallel=data_parallel,
+                           overlap_allreduce=overlap)
     eng.attach(opt)
     eng._set_seed(seed)
     (D.real_loss(D(real.to(dev))[0]) + D.fake_loss(D(fake.to(dev))[0])).backward()
@@ -48,6 +49,11 @@ def _worker(rank, world, port, B, ret):
     both = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(both, flat)
     identical = all(torch.equal(both[0], b) for b in both[1:])
+    # the bucketed, overlapped allreduce (clip() reduces finished layers while the others are still contracting) gives
+    # the same gradients as the single allreduce in step()
+    grads_o, eng_o = _step(D, real[lo:hi], fake[lo:hi], hi - lo, f"cuda:{rank}", True, overlap=True)
+    assert eng_o._reduce_buckets() is not None
+    identical = identical and all(torch.allclose(a, b, rtol=1e-6, atol=1e-8) for a, b in zip(grads, grads_o))
     if rank == 0:
         full, _ = _step(D, real, fake, B, "cuda:0", False)
         err = max(((a - b).norm() / (b.norm() + 1e-12)).item() for a, b in zip(grads, full))
