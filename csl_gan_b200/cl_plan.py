@@ -146,7 +146,10 @@ class ClLayerPlan:
                L.ptr(self.Xt), self.x_rows, slot0, L.ptr(bias_rows), L.ptr(sumsq), L.stream_ptr(t.device))
 
     def _stage_y(self, t: torch.Tensor, slot0: int, scale: float):
-        t = _channels_fastest(t)
+        if not (self.half and self.plan.merged == 2):
+            # (the window-folded capture copies the image rows to shared memory through any strides: an NCHW image
+            # batch needs no layout conversion pass)
+            t = _channels_fastest(t)
         st = L.stream_ptr(t.device)
         if self.kind == "linear":
             # Q = 1: Yt is [p/32][slot][p%32], the same chunked row layout as Xt; the row kernel also

@@ -14,6 +14,7 @@
 #include "ghost2.cuh"
 #include "cl.cuh"
 #include "cl_pair.cuh"
+#include "stage2.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -299,6 +300,30 @@ static bool fused_enabled() {
   return on;
 }
 
+// FP16 capture route: 2 = two sweeps inside one kernel (stage2.cuh, default), 1 = sample held in registers (cl.cuh's
+// single-pass kernels), 0 = separate absmax kernel + staging kernel.  CSLGAN_STAGE=sweep|fused|two is the A/B switch.
+static int stage_route() {
+  static const int r = [] {
+    const char* e = getenv("CSLGAN_STAGE");
+    if (e && !strcmp(e, "fused")) return 1;
+    if (e && !strcmp(e, "two")) return 0;
+    return 2;
+  }();
+  return fused_enabled() ? r : 0;
+}
+
+// CTAs per sample (a power of two <= 8, = the cluster size) and float4 per CTA (a multiple of 256) of the two-sweep
+// capture: about CSLGAN_SWEEP_PER (default 4096 = 16 per thread per sweep;
+// measured 1024 / 2048 / 4096 / 8192: 4096 is the fastest on every CelebA layer) float4 per CTA, more when 8 CTAs are not enough
+static void sweep_split(long long len4, int* parts, int* per) {
+  static const int target = [] { const char* e = getenv("CSLGAN_SWEEP_PER"); int v = e ? atoi(e) : 0; return v >= 256 ? v : 4096; }();
+  int p = 1;
+  while (p < 8 && static_cast<long long>(p) * target < len4) p *= 2;
+  long long q = (len4 + p - 1) / p;
+  q = (q + 255) / 256 * 256;
+  *parts = p; *per = static_cast<int>(q);
+}
+
 // capture kernels of the channels-last path for either element type
 template <typename T>
 int stage_xt_t(const float* src, long long sn, long long sm, long long sh, long long sw, int B, int M, int Ho, int Wo,
@@ -335,8 +360,19 @@ int stage_xt_t(const float* src, long long sn, long long sm, long long sh, long 
     if (!amax || !inv) return fail("FP16 staging needs the amax scratch and the inverse-scale output");
     // single pass when the sample is a dense channels-last block that a cluster of <= 8 CTAs can hold in registers
     const int mv = M / 4;
+    const bool dense_cl = sm == 1 && (M % 4) == 0 && mv <= cg::kFusedThreads && (cg::kFusedThreads % mv) == 0 && sw == M &&
+                          (Ho == 1 || sh == static_cast<long long>(Wo) * M) && (sn % 4) == 0 && B <= (1 << 24) &&
+                          (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    if (stage_route() == 2 && dense_cl && M <= 1024 && static_cast<long long>(Q) * mv < (1LL << 30)) {
+      int sp, per;
+      sweep_split(static_cast<long long>(Q) * mv, &sp, &per);
+      if (launch_clustered(cg::stage_xt_sweep_kernel, B * sp, sp, stream, src, sn, M, Q, scale,
+                           reinterpret_cast<__half*>(dst), rows_total, slot0, bias_rows, inv, sp, per)) return 1;
+      CG_LAUNCH_CHECK();
+      return 0;
+    }
     const int parts = fused_parts(static_cast<long long>(Q) * M);
-    if (fused_enabled() && sm == 1 && (M % 4) == 0 && mv <= cg::kFusedThreads && (cg::kFusedThreads % mv) == 0 && sw == M &&
+    if (stage_route() == 1 && sm == 1 && (M % 4) == 0 && mv <= cg::kFusedThreads && (cg::kFusedThreads % mv) == 0 && sw == M &&
         (Ho == 1 || sh == static_cast<long long>(Wo) * M) && (sn % 4) == 0 && parts > 0 && B <= (1 << 24) &&
         (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
       if (launch_clustered(cg::stage_xt_fused_kernel, B * parts, parts, stream, src, sn, M, Q, scale,
@@ -381,6 +417,67 @@ int stage_xt_t(const float* src, long long sn, long long sm, long long sh, long 
   return 0;
 }
 
+// Thin inputs with the whole window folded into the channel axis (plan->merged == 2), FP16: stage2.cuh's shared-memory
+// im2col.  Returns 0 = launched, 1 = geometry not covered (caller falls back), -1 = error (message set).
+int stage_yt_window(const float* src, long long sn, long long sc, long long sh, long long sw, int B, const cg_unfold_geom* g,
+                    const cg_cl_plan* plan, float scale, __half* dst, int n_slots_total, int slot0, float* inv,
+                    int sm_count, cg_stream_t stream) {
+  const int n_oct = (plan->Cs + 7) / 8;
+  if (plan->merged != 2 || plan->cw != 64 || n_oct > 32 || B > (1 << 24)) return 1;
+  const long long span = static_cast<long long>(g->C - 1) * sc + static_cast<long long>(g->H - 1) * sh +
+                         static_cast<long long>(g->W - 1) * sw;
+  if (sc < 0 || sh < 0 || sw < 0 || span >= (1LL << 31)) return 1;
+  cg::YwParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.C = g->C; p.H = g->H; p.W = g->W;
+  p.sn = sn; p.sc = sc; p.sh_ = sh; p.sw_ = sw;
+  p.KH = g->KH; p.KW = g->KW; p.sth = g->sh; p.stw = g->sw; p.ph = g->ph; p.pw = g->pw; p.dh = g->dh; p.dw = g->dw;
+  p.Ho = g->Ho; p.Wo = g->Wo;
+  p.Cs = plan->Cs; p.n_oct = n_oct;
+  p.Wp = (g->Wo - 1) * g->sw + (g->KW - 1) * g->dw + 1;
+  p.scale = scale; p.slot0 = slot0;
+  p.slot_stride = plan->slot_stride;
+  p.chunk_stride = plan->slot_stride * n_slots_total;
+  // output rows per CTA: as few CTAs per sample as a 64 KB shared image and a covered machine allow (measured at
+  // B = 512 on the 3 x 64 x 64 image: 60 / 64 / 82 / 111 us for 1 / 2 / 4 / 8 CTAs per sample -- halo rows and the
+  // cluster exchange cost more than the extra CTAs bring)
+  auto smem_for = [&](int parts) {
+    const int rpp = (g->Ho + parts - 1) / parts;
+    const long long rows = static_cast<long long>(rpp - 1) * g->sh + static_cast<long long>(g->KH - 1) * g->dh + 1;
+    return rows * p.Wp * g->C * static_cast<long long>(sizeof(float));
+  };
+  static const int want = [] { const char* e = getenv("CSLGAN_WINDOW_PARTS"); return e ? atoi(e) : 0; }();
+  int parts = 1;
+  while (parts < 8 && g->Ho >= 2 * parts &&
+         (static_cast<long long>(B) * parts < 2LL * sm_count || smem_for(parts) > 64 * 1024)) parts *= 2;
+  if (want == 1 || want == 2 || want == 4 || want == 8) parts = want;
+  const long long smem = smem_for(parts);
+  if (smem > 200 * 1024) return 1;
+  p.rpp = (g->Ho + parts - 1) / parts;
+  p.rows_max = static_cast<int>(smem / (static_cast<long long>(p.Wp) * g->C * sizeof(float)));
+  static long long attr_smem[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { fail("cudaGetDevice failed"); return -1; }
+  if (smem > attr_smem[dev]) {
+    if (cudaFuncSetAttribute(cg::stage_yt_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess) { fail("stage_yt_window: shared memory attribute"); return -1; }
+    attr_smem[dev] = smem;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(B) * parts);
+  cfg.blockDim = dim3(32 * n_oct);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = S(stream);
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = static_cast<unsigned>(parts); at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, cg::stage_yt_window_kernel, src, p, dst, inv, parts);
+  if (e != cudaSuccess) { fail("stage_yt_window launch: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
 template <typename T>
 int stage_yt_t(const float* src, long long sn, long long sc, long long sh, long long sw, int B, const cg_unfold_geom* g,
                const cg_cl_plan* plan, float scale, T* dst, int n_slots_total, int slot0, unsigned int* amax,
@@ -419,7 +516,23 @@ int stage_yt_t(const float* src, long long sn, long long sc, long long sh, long 
     // single pass when the sample is a dense NHWC block that a cluster of <= 8 CTAs can hold in registers
     const int parts = fused_parts(static_cast<long long>(g->C) * g->H * g->W);
     const int cvn = g->C / 4;
-    if (fused_enabled() && vec4 && sw == g->C && sh == static_cast<long long>(g->W) * g->C && parts > 0 && B <= (1 << 24) &&
+    const bool dense_nhwc = vec4 && sw == g->C && sh == static_cast<long long>(g->W) * g->C && B <= (1 << 24) &&
+                            cvn <= cg::kFusedThreads && (cg::kFusedThreads % cvn) == 0 && g->H <= cg::kYtFusedMaxDim &&
+                            g->W <= cg::kYtFusedMaxDim;
+    if (stage_route() == 2 && dense_nhwc && static_cast<long long>(g->H) * g->W * cvn < (1LL << 30)) {
+      int sp, per;
+      sweep_split(static_cast<long long>(g->H) * g->W * cvn, &sp, &per);
+      if (launch_clustered(cg::stage_yt_sweep_kernel, B * sp, sp, stream, src, p, reinterpret_cast<__half*>(dst), inv,
+                           sp, per)) return 1;
+      CG_LAUNCH_CHECK();
+      return 0;
+    }
+    if (stage_route() == 2 && plan->merged == 2) {
+      const int rc = stage_yt_window(src, sn, sc, sh, sw, B, g, plan, scale, reinterpret_cast<__half*>(dst), n_slots_total,
+                                     slot0, inv, d.sm, stream);
+      if (rc <= 0) return -rc;                            // 0: launched, < 0: error; > 0: geometry not covered, fall through
+    }
+    if (stage_route() == 1 && vec4 && sw == g->C && sh == static_cast<long long>(g->W) * g->C && parts > 0 && B <= (1 << 24) &&
         cvn <= cg::kFusedThreads && (cg::kFusedThreads % cvn) == 0 && g->H <= cg::kYtFusedMaxDim &&
         g->W <= cg::kYtFusedMaxDim) {
       if (launch_clustered(cg::stage_yt_fused_kernel, B * parts, parts, stream, src, p, reinterpret_cast<__half*>(dst), inv,

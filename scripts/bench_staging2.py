@@ -9,10 +9,12 @@ from csl_gan_b200.grad_sample import LayerPlan
 B = 512
 dev = "cuda"
 layers = [("blocks.0", 3, 64, 64), ("blocks.1", 64, 128, 32), ("blocks.2", 128, 256, 16), ("blocks.3", 256, 512, 8)]
-print("fused" if os.environ.get("CSLGAN_FUSED_STAGE", "1") != "0" else "two-pass")
+print("route", os.environ.get("CSLGAN_STAGE", "sweep"), "per", os.environ.get("CSLGAN_SWEEP_PER", "2048"))
 for name, cin, cout, h in layers:
     conv = torch.nn.Conv2d(cin, cout, 5, stride=2, padding=2).to(dev)
-    act = torch.randn(B, cin, h, h, device=dev).contiguous(memory_format=torch.channels_last)
+    act = torch.randn(B, cin, h, h, device=dev)
+    if cin > 3:
+        act = act.contiguous(memory_format=torch.channels_last)      # (the image batch arrives NCHW)
     bp = torch.randn(B, cout, h // 2, h // 2, device=dev).contiguous(memory_format=torch.channels_last)
     plan = LayerPlan(name, conv, 0, 1)
     plan.capture_activation(act, 0, B, 2)
