@@ -157,6 +157,8 @@ def oracle_sums_from_captures(D_cpu, caps_cpu, B, C, chunk=CPU_CHUNK):
 def verify(eng, D, caps, batch_grads, cfg, B, world, rank, dist_on, wl, tol=1e-3):
     """Outside the timed regions: is what gets timed also right?  """
     out = {"tol": tol}
+    overlap = getattr(eng, "overlap_allreduce", False)
+    eng.overlap_allreduce = False                  # first the plain route: local sums, then ONE allreduce in step()
     eng.ingest_captures(caps)
     fac = eng.clipping_factors()
     any_clip = bool((fac < 1.0).any().item())
@@ -196,10 +198,24 @@ def verify(eng, D, caps, batch_grads, cfg, B, world, rank, dist_on, wl, tol=1e-3
         allc = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         out["replicas_identical"] = all(int(c.item()) == int(allc[0].item()) for c in allc)
+        if overlap:
+            # the timed route: clip() all-reduces finished buckets while the remaining GEMMs run; same gradients
+            eng.overlap_allreduce = True
+            eng.ingest_captures(caps)
+            eng.clip()
+            eng.accum_grads_across_passes()
+            eng.accumulate_batch()
+            eng.noise_multiplier = 0.0
+            eng.step()
+            eng.noise_multiplier = sigma
+            eng.steps -= 1
+            got2 = torch.cat([p.grad.detach().reshape(-1) for p in D.parameters()])
+            out["overlapped_vs_single_allreduce_max_rel_err"] = _rel_err(got2, got)
     else:
         out["step_vs_local_sum_max_rel_err"] = _rel_err(got, torch.cat([t.reshape(-1) for t in local]) / float(B))
     errs = [v for k, v in out.items() if k.endswith("max_rel_err")]
     out["ok"] = bool(all(e < tol for e in errs) and out.get("replicas_identical", True))
+    eng.overlap_allreduce = overlap
     for p in D.parameters():
         p.grad = None
     return out
@@ -497,11 +513,14 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
                              capturable=True, fused=os.environ.get("CSLGAN_FUSED_ADAM", "1") == "1")
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=cfg["sample_size"], noise_multiplier=cfg["sigma"],
                            max_grad_norm=cfg["C"], accum_passes=False, num_private_passes=1,
-                           auto_clip_and_accum_on_step=False, data_parallel=dist_on)
+                           auto_clip_and_accum_on_step=False, data_parallel=dist_on,
+                           overlap_allreduce=dist_on and os.environ.get("CSLGAN_OVERLAP", "1") == "1")
     eng.disable_hooks()
     eng.attach(opt_d)
     eng._set_seed(1234)
-    out = {"clipping": "per-layer" if isinstance(cfg["C"], list) else "flat", "sigma": cfg["sigma"],
+    out = {"allreduce": ("bucketed, overlapped with the clipped-sum GEMMs" if eng.overlap_allreduce else
+                         "one allreduce in step()") if dist_on else None,
+           "clipping": "per-layer" if isinstance(cfg["C"], list) else "flat", "sigma": cfg["sigma"],
            "operand_dtype": eng.operand_dtype,
            "arithmetic": ("FP16 tensor-core operands (10-bit mantissa like TF32; exact per-sample power-of-two scale, "
                           "round-to-nearest staged), fp32 accumulation in TMEM and fp32 everywhere else"
@@ -719,7 +738,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl, "per_gpu_batch": B, "global_batch": B * world, "n_passes": 2,
                        "contractions_per_step": 2 * B * world, "clipping": m["clipping"],
-                       "sigma": m["sigma"], "parallelism": f"dp{world}",
+                       "sigma": m["sigma"], "parallelism": f"dp{world}", "allreduce": m["allreduce"],
                        "arithmetic": m["arithmetic"],
                        "l2": "staged operands per step exceed the 126 MB L2 (no flush needed)" if wl == "celeba_d64_gc"
                              else "working set fits in L2; MNIST is launch-latency bound (SURVEY.md §8d)"},

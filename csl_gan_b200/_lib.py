@@ -109,6 +109,10 @@ _PROTOS = {
     "cg_stage_yt_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                 C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_thin_direct_ok": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int]),
+    "cg_thin_capture": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p,
+                                  C.c_int, C.POINTER(UnfoldGeom), C.c_int, C.c_float, C.c_void_p, C.c_longlong,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_clip_mult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_scale_slots_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p]),
@@ -156,7 +160,7 @@ EXPORTED_SYMBOLS = tuple(_PROTOS)
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # number of ABI calls that enqueue GPU work (bench.py reports it)
 _NO_LAUNCH = {"cg_version", "cg_last_error", "cg_device_info", "cg_plan_unfold", "cg_plan_ghost", "cg_plan_cl",
-              "cg_plan_cl_cw", "cg_cl_pair_ok", "cg_cl_kblock_rows"}
+              "cg_plan_cl_cw", "cg_cl_pair_ok", "cg_cl_kblock_rows", "cg_thin_direct_ok"}
 
 
 def load() -> C.CDLL:
@@ -234,6 +238,11 @@ def noise_multi(segs, in_div, in_div_dev, noise_div, noise_div_dev, seed, offset
 def cl_pair_ok(M: int, geom, plan) -> bool:
     """May cg_cl_contract run this layer's clipped sum on CTA pairs (cg_cl_desc.pair = 1)?"""
     return bool(load().cg_cl_pair_ok(int(M), C.byref(geom), C.byref(plan)))
+
+
+def thin_direct_ok(geom, M: int) -> bool:
+    """Can cg_thin_capture compute this layer's per-sample gradients straight from the critic's tensors?"""
+    return bool(load().cg_thin_direct_ok(C.byref(geom), int(M)))
 
 
 def stream_ptr(device=None) -> int:

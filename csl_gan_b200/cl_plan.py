@@ -96,13 +96,25 @@ class ClLayerPlan:
         self.plan = L.plan_cl(self.geom, (2 if self.half else 1) if merged else 0, cw)
         self.n_planes = self.plan.n_rh * self.plan.n_rw
         self.kblock = L.cl_kblock_rows(self.geom, self.half)      # (rows, slots) per k-block of the clipped sum
+        self.ldT = self.plan.n_taps * self.plan.Cs
+        # thin layers: materialise the (small) per-sample gradients once instead of contracting twice
+        self.thin = (self.kind != "linear" and not ghost_ok and self.Q >= 256 and M * self.ldT <= 16384)
+        # ... and, where csrc/thin.cuh covers the geometry, straight from the critic's own tensors at capture time:
+        # nothing of this layer is staged in HBM (CSLGAN_THIN_DIRECT=0 is the A/B switch)
+        self.direct = bool(self.thin and self.half and self.kind == "conv" and self.plan.merged == 2
+                           and os.environ.get("CSLGAN_THIN_DIRECT", "1") != "0" and L.thin_direct_ok(self.geom, M))
         # chunk-major staging: Xt[m/cw][slot*Q + q][cw], Yt[plane*n_cb + c/cw][slot][hs][ws][cw]
         self.x_chunks = _round_up(M, cw) // cw
         self.x_rows = S * self.Q
-        self.Xt = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
-        self.Xc = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
         self.n_cb = self.plan.Cp // cw
-        self.Yt = torch.zeros(self.n_planes * self.n_cb * S * self.plan.slot_stride, device=dev, dtype=dt)
+        if self.direct:
+            self.Xt = self.Xc = self.Yt = None
+            self.gnorm2 = torch.zeros(S, device=dev)
+            self._act = {}
+        else:
+            self.Xt = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
+            self.Xc = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
+            self.Yt = torch.zeros(self.n_planes * self.n_cb * S * self.plan.slot_stride, device=dev, dtype=dt)
         if self.half:
             # per-slot inverse staging scales (true value = staged * inv), absmax scratch, clipped-sum multipliers
             self.inv_x = torch.ones(S, device=dev)
@@ -117,12 +129,9 @@ class ClLayerPlan:
             self.bsq = torch.zeros(S, device=dev)
         # gradient-natural accumulation buffer T[m][tap][c'] (== parameter layout for Linear and for
         # channels_last conv weights when kw is not merged)
-        self.ldT = self.plan.n_taps * self.plan.Cs
         self.T = torch.zeros((M, self.ldT), device=dev)
         # ghost norms when Q | 128 (needs the un-merged plan, which is what small-Q layers have)
         self.ghost = ghost_ok
-        # thin layers: materialise the (small) per-sample gradients once instead of contracting twice
-        self.thin = (self.kind != "linear" and not self.ghost and self.Q >= 256 and M * self.ldT <= 16384)
         self.Gs = torch.zeros((S, M * self.ldT), device=dev) if self.thin else None
         self._gs_joint = 1
         # clipped-sum GEMM on CTA pairs (cta_group::2) where the layer is wide enough; CSLGAN_NO_PAIR=1 is the
@@ -171,6 +180,9 @@ class ClLayerPlan:
 
     def capture_activation(self, act: torch.Tensor, pass_idx: int):
         slot0 = pass_idx * self.Bpad
+        if self.direct:
+            self._act[pass_idx] = act                  # read by cg_thin_capture when the backprops arrive
+            return
         if self.kind == "convT":
             self._stage_x(act, slot0, 1.0, None, None)
         else:
@@ -178,6 +190,16 @@ class ClLayerPlan:
 
     def capture_backprop(self, g: torch.Tensor, pass_idx: int, scale: float):
         slot0 = pass_idx * self.Bpad
+        if self.direct:
+            act = self._act.pop(pass_idx, None)
+            if act is None or act.shape[0] != g.shape[0]:
+                raise L.CslGanCudaError(f"{self.name}: backprops of pass {pass_idx} arrived without their activation")
+            g = g.contiguous(memory_format=torch.channels_last)       # dense [B][Ho*Wo][M]; a no-op for a channels_last critic
+            sn, sc, sh, sw = _strides4(act)
+            L.call("cg_thin_capture", L.ptr(act), sn, sc, sh, sw, L.ptr(g), g.shape[0], C.byref(self.geom), self.M, scale,
+                   L.ptr(self.Gs[slot0:]), self.Gs.shape[1], L.ptr(self.gnorm2[slot0:]),
+                   L.ptr(self.bias_rows[slot0:]) if self.bias_rows is not None else None, L.stream_ptr(g.device))
+            return
         if self.kind == "convT":
             self._stage_y(g, slot0, scale)
             if self.bias_rows is not None:
@@ -237,6 +259,10 @@ class ClLayerPlan:
         d = self._desc(self.Xt)
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
         d.n_seg, d.seg_stride = n_joint, self.Bpad
+        if self.direct:
+            norm2_row[slot0:slot0 + B].copy_(self.gnorm2[slot0:slot0 + B])
+            self._gs_joint = 1
+            return
         if self.thin:
             # G[slot][m][tap][c'] once (joint mode: the per-sample sum over passes lands in pass 0's slots);
             # the norms are then a row reduction over |theta_layer| floats per sample
@@ -367,6 +393,10 @@ class ClLayerPlan:
     def materialize(self, pass_idx: int, B: int) -> torch.Tensor:
         slot0 = pass_idx * self.Bpad
         w = self.layer.weight
+        if self.direct:
+            # Gs[slot][m][kh][kw][c] -> [B][m][c][kh][kw]
+            return (self.Gs[slot0:slot0 + B].view(B, self.M, self.KH, self.KW, self.Cn).permute(0, 1, 4, 2, 3)
+                    .contiguous())
         out = torch.zeros((B,) + tuple(w.shape), device=w.device)
         st = L.stream_ptr(w.device)
         if self.kind == "linear":

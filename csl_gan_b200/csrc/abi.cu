@@ -15,6 +15,7 @@
 #include "cl.cuh"
 #include "cl_pair.cuh"
 #include "stage2.cuh"
+#include "thin.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -954,6 +955,91 @@ int cg_stage_yt_h(const float* src, long long sn, long long sc, long long sh, lo
                   int slot0, unsigned int* amax, float* inv, cg_stream_t stream) {
   return stage_yt_t<__half>(src, sn, sc, sh, sw, B, g, plan, scale, static_cast<__half*>(dst_half), n_slots_total,
                             slot0, amax, inv, stream);
+}
+
+// ---- thin first convolution: per-sample gradients straight from the critic's tensors (thin.cuh) ------------------
+namespace {
+int thin_fill(const cg_unfold_geom* g, int M, cg::ThinParams* p) {
+  memset(p, 0, sizeof(*p));
+  const int Q = g->Ho * g->Wo;
+  const int Cs = g->KH * g->KW * g->C;
+  const int n_ch = M / 32;
+  if (Cs > 128 || M % 32 || (n_ch != 1 && n_ch != 2 && n_ch != 4) || Q % cg::kThinKb || g->Wo % 4 || g->Wo > cg::kThinKb * 64) return 1;
+  if (g->ph < 0 || g->pw < 0) return 1;
+  p->C = g->C; p->H = g->H; p->W = g->W;
+  p->KH = g->KH; p->KW = g->KW; p->sth = g->sh; p->stw = g->sw; p->ph = g->ph; p->pw = g->pw; p->dh = g->dh; p->dw = g->dw;
+  p->Ho = g->Ho; p->Wo = g->Wo;
+  p->Cs = Cs; p->n_g = (Cs + 7) / 8;
+  p->Hp = (g->Ho - 1) * g->sh + (g->KH - 1) * g->dh + 1;
+  p->Wp = (g->Wo - 1) * g->sw + (g->KW - 1) * g->dw + 1;
+  p->Wp += p->Wp & 1;                                  // even rows and planes: 8-byte cp.async for dense image rows
+  // plane stride: the channels of one tap land ~10 banks apart (the lanes of a builder warp read c' = 8g + lane%8)
+  int P = p->Hp * p->Wp;
+  while ((P % 32) != 10 && (P % 32) != 22) ++P;
+  p->P = P;
+  p->Hc = g->H < p->Hp - g->ph ? g->H : p->Hp - g->ph;
+  p->Wc = g->W < p->Wp - g->pw ? g->W : p->Wp - g->pw;
+  if (p->Hc <= 0 || p->Wc <= 0) return 1;
+  p->M = M; p->n_ch = n_ch; p->Q = Q; p->nkb = Q / cg::kThinKb;
+  p->b_bytes = n_ch * cg::kThinKb * 128;
+  p->a_bytes = 2 * p->n_g * 1024;
+  p->stage_bytes = p->b_bytes + p->a_bytes;
+  p->img_floats = (g->C * P + 3) / 4 * 4;
+  int cols = 32;
+  while (cols < 2 * M) cols *= 2;
+  p->tmem_cols = cols;
+  return 0;
+}
+long long thin_smem(const cg::ThinParams& p) {
+  // tiles (+ the 128-row reads of the last atom stay inside the image buffers) + images + tables + barriers
+  // (small images: explicit slack so that those reads still end inside the allocation)
+  const long long over = (16LL - p.n_g) * 1024 - 2LL * p.img_floats * 4;
+  return 1024LL + static_cast<long long>(cg::kThinStages) * p.stage_bytes + 2LL * p.img_floats * 4 + 128 * 4 + 128 * 4 + 256 +
+         (over > 0 ? over : 0);
+}
+}  // namespace
+
+int cg_thin_direct_ok(const cg_unfold_geom* g, int M) {
+  if (!g) return 0;
+  cg::ThinParams p;
+  if (thin_fill(g, M, &p)) return 0;
+  return thin_smem(p) <= 227 * 1024 ? 1 : 0;
+}
+
+int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long a_sh, long long a_sw, const float* bp,
+                    int B, const cg_unfold_geom* g, int M, float scale, float* Gs, long long gs_stride, float* norm2,
+                    float* bias_rows, cg_stream_t stream) {
+  if (!act || !bp || !g || !Gs || !norm2) return fail("null argument");
+  if (B <= 0) return 0;
+  cg::ThinParams p;
+  if (!cg_thin_direct_ok(g, M) || thin_fill(g, M, &p)) return fail("cg_thin_capture: geometry not covered (cg_thin_direct_ok)");
+  if (static_cast<long long>(B) * p.Q >= (1LL << 31)) return fail("cg_thin_capture: batch too large");
+  p.act = act; p.a_sn = a_sn; p.a_sc = a_sc; p.a_sh = a_sh; p.a_sw = a_sw;
+  p.B = B; p.scale = scale;
+  p.Gs = Gs; p.gs_stride = gs_stride; p.norm2 = norm2; p.bias_rows = bias_rows;
+  DevInfo dv;
+  if (dev_info(&dv)) return 1;
+  CG_CHECK(cudaMemsetAsync(norm2, 0, sizeof(float) * B, S(stream)));
+  // bp: dense channels-last [B*Q rows][M]; box = {32 ch, 64 rows, all chunks} lands as [chunk][row][32 ch]
+  CUtensorMap tb;
+  {
+    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(B) * p.Q, static_cast<cuuint64_t>(p.n_ch)};
+    cuuint64_t str[2] = {static_cast<cuuint64_t>(M) * 4, 128};
+    cuuint32_t box[3] = {32, static_cast<cuuint32_t>(cg::kThinKb), static_cast<cuuint32_t>(p.n_ch)};
+    if (make_tmap_nd(&tb, bp, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, false)) return 1;
+  }
+  const int smem = static_cast<int>(thin_smem(p));
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CG_CHECK(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    CG_CHECK(cudaFuncSetAttribute(cg::thin_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  const int grid = B < dv.sm ? B : dv.sm;
+  cg::thin_direct_kernel<<<grid, cg::kThinThreads, smem, S(stream)>>>(tb, p);
+  CG_LAUNCH_CHECK();
+  return 0;
 }
 
 int cg_clip_mult(const float* factor, const float* inv_x, const float* inv_y, int slot_lo, int slot_hi, float* mult,

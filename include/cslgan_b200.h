@@ -236,6 +236,23 @@ int cg_stage_xt_h(const float* src, long long sn, long long sm, long long sh, lo
 int cg_stage_yt_h(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
                   const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, void* dst_half, int n_slots_total,
                   int slot0, unsigned int* amax, float* inv, cg_stream_t stream);
+/* Thin first convolution (few input channels, large window grid: the 3 -> 64 channel conv of the CelebA critics):
+ * per-sample weight gradients, their squared norms and the per-sample bias gradients in ONE kernel that reads the
+ * layer's own tensors -- no staged operands (csrc/thin.cuh).  Replaces, for such a layer, the fork's
+ * _capture_activations / _capture_backprops + _compute_conv_grad_sample + calc_sample_norms (reference
+ * train.py:382-387, 311-314).
+ *   act   image batch [B][C][H][W] through strides (elements; any layout)
+ *   bp    the layer's grad_output, dense channels-last [B][Ho*Wo][M] fp32, 16-byte aligned
+ *   Gs    [B][M][KH*KW*C] (sample stride gs_stride floats): scale * gradient in the gradient-natural layout
+ *         out[m][kh][kw][c] (= the memory of a channels_last conv weight)
+ *   norm2 [B] ||Gs[n]||^2        bias_rows [B][M] scale * sum over positions of bp (may be NULL)
+ * TF32 operands (rounded to nearest in shared memory), fp32 accumulation.  cg_thin_direct_ok: 1 when the geometry is
+ * covered (KH*KW*C <= 128, M in {32, 64, 128}, Ho*Wo % 64 == 0, Wo % 4 == 0, image + tiles fit in shared memory). */
+int cg_thin_direct_ok(const cg_unfold_geom* g, int M);
+int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long a_sh, long long a_sw, const float* bp,
+                    int B, const cg_unfold_geom* g, int M, float scale, float* Gs, long long gs_stride, float* norm2,
+                    float* bias_rows, cg_stream_t stream);
+
 /* mult[s] = factor[s] * inv_x[s] * inv_y[s] / 2^E for s in [slot_lo, slot_hi), out_scale[0] = 2^E with 2^E the
  * smallest power of two above max_s factor*inv_x*inv_y (so mult <= 1 and the scaled operand stays in FP16 range;
  * samples far below the largest contribution lose low bits they could not contribute to the sum anyway).

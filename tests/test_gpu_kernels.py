@@ -460,3 +460,42 @@ def test_fp16_operands_survive_a_wide_dynamic_range(layer):
     gs = plan.materialize(0, B).cpu().double()
     for n in range(B):
         assert ((gs[n] - gw_ref[n]).norm() / gw_ref[n].norm()).item() < 1e-3, n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# thin first convolution straight from the critic's tensors (csrc/thin.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p,d,layout", [
+    (5, 3, 64, 64, 64, 5, 2, 2, 1, "nchw"),        # D64 blocks.0, image as the data loader delivers it
+    (5, 3, 64, 64, 64, 5, 2, 2, 1, "nhwc"),        # ... and as a channels_last critic sees it
+    (300, 3, 64, 64, 64, 5, 2, 2, 1, "nchw"),      # more samples than SMs: several items per CTA, both image buffers
+    (3, 1, 32, 32, 32, 3, 1, 1, 1, "nchw"),        # one channel, stride 1, M = 32 (one chunk)
+    (2, 4, 128, 32, 32, 4, 2, 1, 1, "nhwc"),       # even kernel, M = 128 (four chunks), 64 staged rows
+    (2, 3, 64, 32, 32, 3, 1, 2, 2, "nchw"),        # dilation 2
+])
+def test_thin_capture_matches_unfold_einsum(B, Cin, Cout, H, W, k, s, p, d, layout):
+    conv, A, Bp, Ho, Wo = _conv_case(B, Cin, Cout, H, W, k, s, p, d, seed=11)
+    geom = L.UnfoldGeom(Cin, H, W, k, k, s, s, p, p, d, d, Ho, Wo)
+    assert L.thin_direct_ok(geom, Cout)
+    scale = 3.0
+    a = A.to(DEV)
+    if layout == "nhwc":
+        a = a.contiguous(memory_format=torch.channels_last)
+    bp = Bp.to(DEV).contiguous(memory_format=torch.channels_last)
+    Cs = k * k * Cin
+    Gs = torch.full((B, Cout * Cs), float("nan"), device=DEV)
+    n2 = torch.full((B,), float("nan"), device=DEV)
+    bias = torch.full((B, Cout), float("nan"), device=DEV)
+    L.call("cg_thin_capture", a.data_ptr(), a.stride(0), a.stride(1), a.stride(2), a.stride(3), bp.data_ptr(), B,
+           C.byref(geom), Cout, scale, Gs.data_ptr(), Gs.shape[1], n2.data_ptr(), bias.data_ptr(), st())
+    torch.cuda.synchronize()
+    # oracle: unfold + einsum in fp64 (reference semantics: opacus _compute_conv_grad_sample)
+    U = F.unfold(A.double(), k, dilation=d, padding=p, stride=s)                    # [B][Cin*k*k][Q], rows (c, kh, kw)
+    G = scale * torch.einsum("bmq,bpq->bmp", Bp.double().reshape(B, Cout, -1), U)   # [B][Cout][(c, kh, kw)]
+    G = G.view(B, Cout, Cin, k, k).permute(0, 1, 3, 4, 2).reshape(B, -1)            # natural layout [m][kh][kw][c]
+    err = ((Gs.cpu().double() - G).norm(dim=1) / G.norm(dim=1)).max().item()
+    assert err < 1e-3, err
+    n2_ref = (G * G).sum(dim=1)
+    assert ((n2.cpu().double() - n2_ref).abs() / n2_ref).max().item() < 2e-3
+    b_ref = scale * Bp.double().sum(dim=(2, 3))
+    assert ((bias.cpu().double() - b_ref).abs().max() / b_ref.abs().max()).item() < 1e-5
