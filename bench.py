@@ -514,7 +514,7 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=cfg["sample_size"], noise_multiplier=cfg["sigma"],
                            max_grad_norm=cfg["C"], accum_passes=False, num_private_passes=1,
                            auto_clip_and_accum_on_step=False, data_parallel=dist_on,
-                           overlap_allreduce=dist_on and os.environ.get("CSLGAN_OVERLAP", "1") == "1")
+                           overlap_allreduce=dist_on and os.environ.get("CSLGAN_OVERLAP", "0") == "1")
     eng.disable_hooks()
     eng.attach(opt_d)
     eng._set_seed(1234)
@@ -572,10 +572,14 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
     prof = L.profile_summary()
     L.set_profile(False)
     per_step = {k: (ms / steps, n // steps) for k, (ms, n) in prof.items()}
-    # the contraction kernels: channels-last MN-major GEMM (main), ghost-norm Gram kernel, kw-plane GEMM (odd geometries)
+    # the contraction kernels: channels-last MN-major GEMM (main), ghost-norm Gram kernel, kw-plane GEMM (odd
+    # geometries) -- tensor bound -- and the thin first conv's capture+contraction kernel, which reads the critic's
+    # fp32 tensors and is HBM bound by design (3 % of the FLOPs, a third of the operand bytes)
     contract_calls = ("cg_cl_contract", "cg_ghost_norm", "cg_contract")
     out["t_contract"] = sum(per_step.get(k, (0.0, 0))[0] for k in contract_calls)
     out["n_contract"] = sum(per_step.get(k, (0.0, 0))[1] for k in contract_calls)
+    out["t_thin"] = per_step.get("cg_thin_capture", (0.0, 0))[0]
+    out["n_thin"] = per_step.get("cg_thin_capture", (0.0, 0))[1]
     out["flops_step"] = 2 * B * cfg["fpsg"]
     out["kernel_ms_per_step"] = {k: round(v[0], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][0])}
     if not do_e2e:
@@ -662,7 +666,21 @@ def roofline_block(m, wl, B, peaks):
     else:
         peak, src = live, f"{dt} torch.matmul 8192^3 best of 12, measured live"
     t_c = m["t_contract"]
-    achieved = m["flops_step"] / (t_c * 1e-3) / 1e12 if t_c > 0 else None
+    flops = m["flops_step"]
+    thin = None
+    if m.get("t_thin", 0.0) > 0 and wl == "celeba_d64_gc":
+        # the first conv (3 -> 64 channels, 5x5, 32x32 windows) runs in cg_thin_capture: its FLOPs leave the tensor
+        # roofline, and it gets its own HBM roofline: bp 4*1024*64 + image 4*3*64*64 read, Gs 4*4800 written per unit
+        thin_flops = 2 * B * (2 * 64 * 75 * 1024)
+        flops -= thin_flops
+        thin_bytes = 2 * B * (4 * 1024 * 64 + 4 * 3 * 64 * 64 + 4 * 4800)
+        hbm = peaks.get("hbm_gbs")
+        ach = thin_bytes / (m["t_thin"] * 1e-3) / 1e9
+        thin = {"bound": "hbm", "kernel": "thin_direct_kernel (capture + contraction + norm of the first conv, tcgen05 kind::tf32)",
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if hbm else None,
+                "algorithmic_bytes_per_step": thin_bytes, "ms_per_step": m["t_thin"], "launches_per_step": m["n_thin"],
+                "algorithmic_flops_per_step": thin_flops}
+    achieved = flops / (t_c * 1e-3) / 1e12 if t_c > 0 else None
     traffic, tnote = None, "no tracked ncu traffic record for this workload / batch"
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
@@ -678,7 +696,8 @@ def roofline_block(m, wl, B, peaks):
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
             "peak_source": src, "live_matmul_peak": {"dtype": dt if dt == "tf32" else "f16", "tflops": live, "clocks": live_clk},
             "bf16_peak_measured": peaks.get("bf16_tflops"),
-            "algorithmic_flops_per_step": m["flops_step"], "contract_ms_per_step": t_c,
+            "algorithmic_flops_per_step": flops, "contract_ms_per_step": t_c,
+            "thin_layer": thin,
             "contract_launches_per_step": m["n_contract"],
             "whole_dp_frac": m["flops_step"] / (m["t_dp"] * 1e-3) / 1e12 / peak,
             "traffic": traffic, "traffic_note": tnote}

@@ -55,6 +55,11 @@ struct ThinParams {
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+// Round-to-nearest TF32 for an operand the tensor core will TRUNCATE to its upper 19 bits (kind::tf32 ignores the low
+// 13 mantissa bits, measured): adding half an ulp to the bit pattern is all that is left to do (carries run into the
+// exponent as they should; Inf becomes NaN, which a gradient containing Inf is anyway).  One instruction instead of
+// the three cvt.rna.tf32.f32 expands to.
+__device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void builder_barrier() {
@@ -258,8 +263,8 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
         for (int i = 0; i < 4; ++i) {
           if (tok[i]) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_base + static_cast<uint32_t>((gq + 4 * i) * 1024)),
-                         "r"(__float_as_uint(round_tf32(v[i][0]))), "r"(__float_as_uint(round_tf32(v[i][1]))),
-                         "r"(__float_as_uint(round_tf32(v[i][2]))), "r"(__float_as_uint(round_tf32(v[i][3]))) : "memory");
+                         "r"(tf32_rn_bits((v[i][0]))), "r"(tf32_rn_bits((v[i][1]))),
+                         "r"(tf32_rn_bits((v[i][2]))), "r"(tf32_rn_bits((v[i][3]))) : "memory");
           }
         }
         mbar_wait(&full_bar[stage], phase);
@@ -271,12 +276,12 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(q0));
           if (two) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(q1));
           b0 += x.x + y.x; b1 += x.y + y.y; b2 += x.z + y.z; b3 += x.w + y.w;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q0), "r"(__float_as_uint(round_tf32(x.x))),
-                       "r"(__float_as_uint(round_tf32(x.y))), "r"(__float_as_uint(round_tf32(x.z))),
-                       "r"(__float_as_uint(round_tf32(x.w))) : "memory");
-          if (two) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q1), "r"(__float_as_uint(round_tf32(y.x))),
-                                "r"(__float_as_uint(round_tf32(y.y))), "r"(__float_as_uint(round_tf32(y.z))),
-                                "r"(__float_as_uint(round_tf32(y.w))) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q0), "r"(tf32_rn_bits((x.x))),
+                       "r"(tf32_rn_bits((x.y))), "r"(tf32_rn_bits((x.z))),
+                       "r"(tf32_rn_bits((x.w))) : "memory");
+          if (two) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(q1), "r"(tf32_rn_bits((y.x))),
+                                "r"(tf32_rn_bits((y.y))), "r"(tf32_rn_bits((y.z))),
+                                "r"(tf32_rn_bits((y.w))) : "memory");
         }
         fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core's reads
         __syncwarp();
