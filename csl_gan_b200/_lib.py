@@ -149,6 +149,9 @@ _PROTOS = {
     "cg_noise_finalize_multi": (C.c_int, [C.POINTER(NoiseSeg), C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_void_p,
                                           C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.POINTER(C.c_ulonglong),
                                           C.c_void_p]),
+    "cg_noise_finalize_allreduce": (C.c_int, [C.POINTER(NoiseSeg), C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_void_p,
+                                              C.POINTER(C.c_ulonglong), C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                              C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "cg_row_l2_norm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_row_l2_norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "cg_vec_max": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
@@ -232,6 +235,28 @@ def noise_multi(segs, in_div, in_div_dev, noise_div, noise_div_dev, seed, offset
     inc = C.c_ulonglong(0)
     call("cg_noise_finalize_multi", arr, len(segs), float(in_div), ptr(in_div_dev), float(noise_div), ptr(noise_div_dev),
          int(seed), int(offset), ptr(offset_dev), C.byref(inc), stream)
+    return inc.value
+
+
+def noise_multi_allreduce(segs, mean: bool, seed, offset, offset_dev, local_flat: torch.Tensor, mc_ptr: int,
+                          peer_ptrs, count_off: int, rank: int, world: int, stream) -> int:
+    """One launch of cg_noise_finalize_allreduce: cross-rank sum + noise + broadcast over the multicast mapping
+    `mc_ptr` of the symmetric buffer `local_flat` (or, mc_ptr = 0, over the peer mappings `peer_ptrs`); `segs` as in
+    noise_multi.  Returns the generator-offset advance."""
+    peers = None
+    if not mc_ptr:
+        peers = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    arr = (NoiseSeg * len(segs))()
+    for i, (tin, tg, mult, sdev) in enumerate(segs):
+        arr[i].inp = ptr(tin)
+        arr[i].grad = ptr(tg)
+        arr[i].n = tg.numel()
+        arr[i].std_mult = float(mult)
+        arr[i].std_dev = ptr(sdev)
+    inc = C.c_ulonglong(0)
+    call("cg_noise_finalize_allreduce", arr, len(segs), 1 if mean else 0, int(seed), int(offset), ptr(offset_dev),
+         C.byref(inc), local_flat.data_ptr(), int(mc_ptr) or None, peers, local_flat.numel(), int(count_off), int(rank),
+         int(world), stream)
     return inc.value
 
 

@@ -1318,10 +1318,13 @@ int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int sl
   return 0;
 }
 
-int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div, const float* in_div_dev,
-                            double noise_div, const float* noise_div_dev, unsigned long long seed,
-                            unsigned long long offset, const unsigned long long* offset_dev,
-                            unsigned long long* offset_inc, cg_stream_t stream) {
+namespace {
+int noise_multi_impl(const cg_noise_seg* segs, int n_segs, double in_div, const float* in_div_dev,
+                     double noise_div, const float* noise_div_dev, unsigned long long seed,
+                     unsigned long long offset, const unsigned long long* offset_dev,
+                     unsigned long long* offset_inc, const float* local_base, float* mc_base, float* const* peers,
+                     long long buf_len, long long count_off, int rank, int world, cg_stream_t stream) {
+  const bool ar = mc_base != nullptr || peers != nullptr;
   if (offset_inc) *offset_inc = 0;
   if (n_segs <= 0) return 0;
   if (!segs) return fail("null segment table");
@@ -1340,6 +1343,12 @@ int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div,
       const cg_noise_seg& in = segs[i];
       if (in.n <= 0) continue;
       if (!in.grad) return fail("segment %d: null output", i);
+      if (ar) {
+        // both operands of every segment must lie inside the symmetric buffer
+        const bool in_ok = !in.in || (in.in >= local_base && in.in + in.n <= local_base + buf_len);
+        const bool out_ok = in.grad >= local_base && in.grad + in.n <= local_base + buf_len;
+        if (!in_ok || !out_ok) return fail("segment %d lies outside the symmetric buffer", i);
+      }
       cg::NoiseSeg& o = p.seg[m++];
       o.in = in.in; o.grad = in.grad; o.n = in.n; o.std_dev = in.std_dev;
       o.std_mult = static_cast<float>(in.std_mult);
@@ -1359,14 +1368,44 @@ int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div,
     p.in_mul = recip(in_div); p.noise_mul = recip(noise_div);
     p.in_div_dev = in_div_dev; p.noise_div_dev = noise_div_dev;
     p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
-    long long grid = blk;
+    p.local_base = local_base; p.mc_base = mc_base; p.count_off = count_off; p.rank = rank; p.world = world;
+    if (peers) for (int r = 0; r < world && r < 8; ++r) p.peer[r] = peers[r];
+    long long grid = ar ? (blk + world - 1) / world : blk;
     const long long cap = static_cast<long long>(d.sm) * 8;
     if (grid > cap) grid = cap;
-    cg::noise_multi_kernel<<<static_cast<unsigned int>(grid), 256, 0, S(stream)>>>(p);
+    if (grid < 1) grid = 1;
+    if (ar) cg::noise_multi_kernel<true><<<static_cast<unsigned int>(grid), 256, 0, S(stream)>>>(p);
+    else cg::noise_multi_kernel<false><<<static_cast<unsigned int>(grid), 256, 0, S(stream)>>>(p);
     CG_LAUNCH_CHECK();
   }
   if (offset_inc) *offset_inc = off;
   return 0;
+}
+}  // namespace
+
+int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div, const float* in_div_dev,
+                            double noise_div, const float* noise_div_dev, unsigned long long seed,
+                            unsigned long long offset, const unsigned long long* offset_dev,
+                            unsigned long long* offset_inc, cg_stream_t stream) {
+  return noise_multi_impl(segs, n_segs, in_div, in_div_dev, noise_div, noise_div_dev, seed, offset, offset_dev, offset_inc,
+                          nullptr, nullptr, nullptr, 0, -1, 0, 1, stream);
+}
+
+int cg_noise_finalize_allreduce(const cg_noise_seg* segs, int n_segs, int mean, unsigned long long seed,
+                                unsigned long long offset, const unsigned long long* offset_dev,
+                                unsigned long long* offset_inc, const float* local_base, float* mc_base,
+                                float* const* peers, long long buf_len, long long count_off, int rank, int world,
+                                cg_stream_t stream) {
+  if (!local_base || (!mc_base && !peers)) return fail("null symmetric base / neither a multicast nor peer mappings");
+  if (world < 1 || rank < 0 || rank >= world) return fail("bad rank %d of %d", rank, world);
+  if (!mc_base && world > 8) return fail("the peer-to-peer exchange covers up to 8 ranks");
+  if (!mc_base && peers[rank] != local_base) return fail("peers[rank] must be this rank's own buffer");
+  if (count_off >= buf_len) return fail("count element outside the buffer");
+  if (mean && count_off < 0) return fail("mean reduction needs the sample-count element");
+  // mean: both divisors are the all-rank sample count the kernel reads through the switch (1.0 only marks them active)
+  return noise_multi_impl(segs, n_segs, mean ? 1.0 : 0.0, nullptr, mean ? 1.0 : 0.0, nullptr, seed, offset, offset_dev,
+                          offset_inc, local_base, mc_base, mc_base ? nullptr : peers, buf_len, mean ? count_off : -1, rank,
+                          world, stream);
 }
 
 int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, double std, double noise_div,

@@ -460,18 +460,100 @@ struct NoiseParams {
   const float* noise_div_dev;
   unsigned long long seed, offset;
   const unsigned long long* offset_dev;
+  // fused allreduce (kAllReduce): every seg.in / seg.grad lies in ONE symmetric buffer that starts at `local_base` on
+  // this rank and is mapped at the NVSwitch multicast address `mc_base` on all `world` ranks
+  const float* local_base;
+  float* mc_base;
+  long long count_off;                 // element of the buffer that holds each rank's live sample count (-1: none)
+  int rank, world;
+  // peer-to-peer variant (mc_base == nullptr): the same buffer on every rank through its NVLink peer mapping; the sum
+  // is formed in rank order from plain 16-byte loads and the result stored to every peer
+  float* peer[8];
 };
 
+
+
+// NVLink SHARP (multimem) accesses on a multicast address: the load returns the SUM of the word over all ranks'
+// copies (reduced inside the switch), the store writes the word into all ranks' copies.
+__device__ __forceinline__ float multimem_ld_sum(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+// 16-byte forms (one NVLink request per four words: the 4-byte forms above ran the exchange at a fifth of this rate)
+__device__ __forceinline__ float4 multimem_ld_sum4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float4 ar_load4(const NoiseParams& p, long long off) {
+  if (p.mc_base) return multimem_ld_sum4(p.mc_base + off);
+  // all loads first (eight independent 16-byte requests in flight per thread), then the sum in rank order
+  float4 b[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    b[r] = r < p.world ? __ldcg(reinterpret_cast<const float4*>(p.peer[r] + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a = b[0];
+#pragma unroll
+  for (int r = 1; r < 8; ++r) {
+    if (r < p.world) { a.x += b[r].x; a.y += b[r].y; a.z += b[r].z; a.w += b[r].w; }
+  }
+  return a;
+}
+__device__ __forceinline__ float ar_load1(const NoiseParams& p, long long off) {
+  if (p.mc_base) return multimem_ld_sum(p.mc_base + off);
+  float a = p.peer[0][off];
+  for (int r = 1; r < p.world; ++r) a += p.peer[r][off];
+  return a;
+}
+__device__ __forceinline__ void ar_store4(const NoiseParams& p, long long off, float4 v) {
+  if (p.mc_base) { multimem_st4(p.mc_base + off, v); return; }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r < p.world) __stcg(reinterpret_cast<float4*>(p.peer[r] + off), v);
+}
+__device__ __forceinline__ void ar_store1(const NoiseParams& p, long long off, float v) {
+  if (p.mc_base) { multimem_st(p.mc_base + off, v); return; }
+  for (int r = 0; r < p.world; ++r) p.peer[r][off] = v;
+}
+
+// kAllReduce = false: grad = in/div + noise on this GPU's own buffers.
+// kAllReduce = true : the data-parallel exchange and the noise in ONE kernel over NVSwitch multicast memory: rank r
+//   owns the work blocks b = r (mod world); for its elements it loads the all-rank sum of the clipped gradients with
+//   multimem.ld_reduce, divides by the all-rank sample count, adds the noise -- drawn from the same Philox counters
+//   the single-GPU launch would use, so only 1/world of the normals is generated per rank -- and multicasts the result
+//   into every rank's gradient (in place).  Callers bracket the launch with cross-rank barriers.
+template <bool kAllReduce>
 __global__ void __launch_bounds__(256, 4)
 noise_multi_kernel(const __grid_constant__ NoiseParams p) {
   float in_mul = p.in_mul, noise_mul = p.noise_mul;
-  if (p.in_div_dev) in_mul = __fdiv_rn(1.0f, p.in_div_dev[0]);
-  if (p.noise_div_dev) noise_mul = __fdiv_rn(1.0f, p.noise_div_dev[0]);
+  if (kAllReduce) {
+    if (p.count_off >= 0) {
+      const float cnt = ar_load1(p, p.count_off);
+      const float r = __fdiv_rn(1.0f, cnt);
+      if (in_mul > 0.f || p.in_div_dev) in_mul = r;
+      if (noise_mul > 0.f || p.noise_div_dev) noise_mul = r;
+    }
+  } else {
+    if (p.in_div_dev) in_mul = __fdiv_rn(1.0f, p.in_div_dev[0]);
+    if (p.noise_div_dev) noise_mul = __fdiv_rn(1.0f, p.noise_div_dev[0]);
+  }
   unsigned long long base = p.offset;
   if (p.offset_dev) base += p.offset_dev[0];
   const unsigned long long base4 = base >> 2;
   const uint2 key = make_uint2(static_cast<unsigned int>(p.seed), static_cast<unsigned int>(p.seed >> 32));
-  for (long long b = blockIdx.x; b < p.n_blocks; b += gridDim.x) {
+  const long long b_first = kAllReduce ? static_cast<long long>(blockIdx.x) * p.world + p.rank : blockIdx.x;
+  const long long b_step = kAllReduce ? static_cast<long long>(gridDim.x) * p.world : gridDim.x;
+  for (long long b = b_first; b < p.n_blocks; b += b_step) {
     int s = 0;
 #pragma unroll 1
     while (s + 1 < p.n_segs && b >= p.seg[s + 1].blk0) ++s;
@@ -481,9 +563,9 @@ noise_multi_kernel(const __grid_constant__ NoiseParams p) {
     const long long idx = (bl - k * sg.tgrid) * 256 + threadIdx.x;
     const long long nthreads = 256LL * sg.tgrid;
     const long long li0 = idx + nthreads * 4 * k;
-    if (li0 >= sg.n) continue;
+    if (!kAllReduce && li0 >= sg.n) continue;
     float zz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (sg.draws) {
+    if (sg.draws && li0 < sg.n) {
       float stdv = sg.std_mult;
       if (sg.std_dev) stdv = __fmul_rn(stdv, sg.std_dev[0]);
       const unsigned long long c = base4 + sg.off4 + static_cast<unsigned long long>(k);
@@ -498,6 +580,44 @@ noise_multi_kernel(const __grid_constant__ NoiseParams p) {
         zz[ii] = __fmul_rn(zz[ii], stdv);                          // torch.normal(0, std): rand * std + 0
         if (noise_mul > 0.f) zz[ii] = __fmul_rn(zz[ii], noise_mul);   // noise /= batch_size (torch CUDA: * 1/B)
       }
+    }
+    if (kAllReduce) {
+      // torch's element order gives a thread four words `nthreads` apart; the exchange wants 16 contiguous bytes per
+      // thread.  The block's work is four runs of 256 consecutive elements: the normals meet in shared memory and
+      // thread t then owns words [4q, 4q+4) of run t/64 (q = t%64) -- one multimem.ld_reduce.v4, one multimem.st.v4.
+      __shared__ float s_z[4][256];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) s_z[ii][threadIdx.x] = zz[ii];
+      __syncthreads();
+      const int run = threadIdx.x >> 6, q4 = (threadIdx.x & 63) << 2;
+      const long long e0 = (bl - k * sg.tgrid) * 256 + nthreads * (4 * k + run) + q4;     // element of the segment
+      if (e0 < sg.n) {
+        const long long oin = sg.in ? (sg.in - p.local_base) + e0 : 0;
+        const long long oout = (sg.grad - p.local_base) + e0;
+        const float4 z = *reinterpret_cast<const float4*>(&s_z[run][q4]);
+        if (e0 + 3 < sg.n && ((oin | oout) & 3) == 0) {
+          float4 v = z;
+          if (sg.in) {
+            v = ar_load4(p, oin);
+            if (in_mul > 0.f) { v.x = __fmul_rn(v.x, in_mul); v.y = __fmul_rn(v.y, in_mul); v.z = __fmul_rn(v.z, in_mul); v.w = __fmul_rn(v.w, in_mul); }
+            if (sg.draws) { v.x = __fadd_rn(v.x, z.x); v.y = __fadd_rn(v.y, z.y); v.z = __fadd_rn(v.z, z.z); v.w = __fadd_rn(v.w, z.w); }
+          }
+          ar_store4(p, oout, v);
+        } else {
+          const float zs[4] = {z.x, z.y, z.z, z.w};
+          for (int j = 0; j < 4 && e0 + j < sg.n; ++j) {
+            float v = zs[j];
+            if (sg.in) {
+              v = ar_load1(p, oin + j);
+              if (in_mul > 0.f) v = __fmul_rn(v, in_mul);
+              if (sg.draws) v = __fadd_rn(v, zs[j]);
+            }
+            ar_store1(p, oout + j, v);
+          }
+        }
+      }
+      __syncthreads();                              // s_z is rewritten by the next work block
+      continue;
     }
     float g[4];
 #pragma unroll

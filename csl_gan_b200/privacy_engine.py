@@ -185,7 +185,7 @@ class PrivacyEngine:
                  data_parallel: bool = False, global_batch_size: Optional[int] = None,
                  per_layer_noise: str = "l2norm", clip_margin: float = 0.0,
                  operand_dtype: Optional[str] = None, overlap_allreduce: bool = False, nccl_reserve_sms: int = 8,
-                 **misc):
+                 fused_allreduce: bool = True, **misc):
         """`batch_size` is THIS rank's batch.  Under data parallelism the accountant needs the global sampling
         rate: pass `global_batch_size`, or leave it None and the constructor sums the per-rank batch sizes with
         one tiny allreduce.
@@ -201,6 +201,11 @@ class PrivacyEngine:
         exact per-sample power-of-two scale (TF32's 10-bit mantissa, half the bytes, twice the MMA rate); "tf32"
         keeps fp32 words.  Joint clipping (accum_passes=True) sums two passes in one accumulator and therefore
         always uses TF32 (the passes' staging scales differ).
+        `fused_allreduce` (data parallel, default on): where the ranks share an NVSwitch multicast mapping
+        (torch.distributed._symmetric_memory), the clipped sums are written into symmetric memory and step() does the
+        cross-rank sum, the noise and the broadcast of the finished gradient in ONE kernel (multimem.ld_reduce /
+        multimem.st); every rank generates only 1/world of the normals.  Falls back to the NCCL allreduce when the
+        mapping is unavailable, a parameter is not a view of the flat buffer, or `overlap_allreduce` is on.
         `overlap_allreduce` (data parallel): clip() walks the layers from the last to the first and all-reduces
         every finished bucket of the flat clipped-sum buffer asynchronously (NCCL stream), so the collective of the
         large late layers runs under the contractions of the early ones; the persistent GEMM kernels launched
@@ -225,6 +230,10 @@ class PrivacyEngine:
         if accum_passes:
             self.operand_dtype = "tf32"
         self.overlap_allreduce = bool(overlap_allreduce)
+        self.fused_allreduce = bool(fused_allreduce)
+        self._symm = None
+        self._symm_failed = False
+        self._symm_last = 1
         self.nccl_reserve_sms = int(nccl_reserve_sms)
         self._reduce_works: list = []
         self._reduced_early = False
@@ -728,7 +737,7 @@ class PrivacyEngine:
         # ONE flat buffer [|theta| + 1]: the parameters' clipped sums are views into it (same strides as the
         # parameter, so channels_last weights keep their layout) and the last element carries the live batch
         # count -> the data-parallel exchange is one allreduce of this buffer, no concatenation
-        flat = torch.empty(self._n_theta + 1, device=self.device)
+        flat = self._new_flat()
         outs, off = [], 0
         for p in self._params:
             dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
@@ -819,6 +828,26 @@ class PrivacyEngine:
                 hi = lo
         return out
 
+    def _new_flat(self) -> torch.Tensor:
+        """The flat clipped-sum buffer of this clip() call.  Data parallel over NVSwitch: one of two buffers in
+        symmetric (multicast-mapped) memory, so step() can sum, noise and broadcast in one kernel; else plain memory."""
+        if self.data_parallel and self.fused_allreduce and self._symm is None and not self._symm_failed:
+            from .dist import SymmetricFlat
+            try:
+                if SymmetricFlat.available(self.process_group):
+                    self._symm = SymmetricFlat(self._n_theta + 1, self.device, self.process_group)
+                else:
+                    self._symm_failed = True
+            except Exception as e:                      # no symmetric allocator / no multicast: keep NCCL
+                self._symm_failed = True
+                self._symm_error = repr(e)
+        if self._symm is not None:
+            busy = self._symm.index_of(self._summed_flat)
+            i = 1 - busy if busy >= 0 else 1 - self._symm_last
+            self._symm_last = i
+            return self._symm.bufs[i]
+        return torch.empty(self._n_theta + 1, device=self.device)
+
     def accum_grads_across_passes(self):
         """Sum the per-pass clipped sums (reference train.py:402).  Already fused into clip()."""
         if self._clipped is None:
@@ -905,7 +934,12 @@ class PrivacyEngine:
         self.steps += 1
         bs = float(self._accum_bs)
         div_dev = None
-        if self.data_parallel:
+        fused_i = -1
+        if (self.data_parallel and self._symm is not None and not self._reduced_early and self._summed_views_intact()):
+            fused_i = self._symm.index_of(self._summed_flat)
+        if fused_i >= 0:
+            pass                                             # exchange + noise in one kernel below
+        elif self.data_parallel:
             if self._reduced_early:
                 # clip() already reduced every bucket (overlap_allreduce): only wait; the count rode along
                 self._wait_reduces()
@@ -923,8 +957,20 @@ class PrivacyEngine:
             else:
                 segs.append((s, s, self.noise_multiplier, self._noise_c_dev[k:k + 1]))
         div = bs if mean else 0.0
-        inc = L.noise_multi(segs, div, div_dev if mean else None, div, div_dev if mean else None, self._seed,
-                            0 if od is not None else self._philox_offset, od, st)
+        if fused_i >= 0:
+            # cross-rank sum, division by the global sample count, noise and broadcast in ONE kernel over the NVSwitch
+            # multicast mapping of the flat buffer; every rank draws only its 1/world share of the normals
+            sy = self._symm
+            flat = self._summed_flat
+            flat[self._n_theta:].fill_(bs)
+            sy.barrier(fused_i)                              # every rank's sums (and count) are written
+            inc = L.noise_multi_allreduce(segs, mean, self._seed, 0 if od is not None else self._philox_offset, od,
+                                          flat, sy.mc_ptrs[fused_i] if sy.use_multicast else 0, sy.peer_ptrs[fused_i],
+                                          self._n_theta, sy.rank, sy.world, st)
+            sy.barrier(fused_i)                              # every rank's share of the result has landed everywhere
+        else:
+            inc = L.noise_multi(segs, div, div_dev if mean else None, div, div_dev if mean else None, self._seed,
+                                0 if od is not None else self._philox_offset, od, st)
         for p in self._params:
             p.grad = p.summed_grad                           # noised in place
             p.summed_grad = None

@@ -412,6 +412,24 @@ int cg_noise_finalize_multi(const cg_noise_seg* segs, int n_segs, double in_div,
                             unsigned long long offset, const unsigned long long* offset_dev,
                             unsigned long long* offset_inc, cg_stream_t stream);
 
+/* Data parallel: the allreduce of the clipped sums AND the noise in one kernel over NVSwitch multicast memory
+ * (replaces NCCL allreduce + cg_noise_finalize_multi; reference: opacus' DistributedDataParallel gradient exchange
+ * followed by the patched step, train.py:484).  Every seg.in / seg.grad must lie inside ONE symmetric buffer of
+ * buf_len floats that starts at local_base on this rank and is mapped at the multicast address mc_base on all `world`
+ * ranks (torch.distributed._symmetric_memory).  Rank r processes the work blocks b = r (mod world): it loads the
+ * all-rank sum with multimem.ld_reduce, divides by the all-rank sum of element count_off (mean = 1; each rank stores
+ * its live sample count there), adds noise from the SAME Philox counters cg_noise_finalize_multi would use -- every
+ * rank generates 1/world of the normals -- and multicasts the result into every rank's buffer (in place).
+ * mc_base == NULL selects the peer-to-peer variant: peers[r] is rank r's buffer through its NVLink peer mapping
+ * (peers[rank] == local_base, world <= 8); the sum is formed in rank order from plain 16-byte loads and the result is
+ * stored to every peer.
+ * The caller brackets the launch with cross-rank barriers (all sums written before / all results visible after). */
+int cg_noise_finalize_allreduce(const cg_noise_seg* segs, int n_segs, int mean, unsigned long long seed,
+                                unsigned long long offset, const unsigned long long* offset_dev,
+                                unsigned long long* offset_inc, const float* local_base, float* mc_base,
+                                float* const* peers, long long buf_len, long long count_off, int rank, int world,
+                                cg_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Per-sample row norms (reference gradient_penalty.py:52-53, 60-61; immediate sensitivity,
  * train.py:457/469) and per-sample L2 clipping (reference backprop_clip.py:18-22)

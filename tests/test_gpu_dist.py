@@ -9,13 +9,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _step(D, real, fake, B, dev, data_parallel, seed=77, sigma=2.0, C=1.5, overlap=False):
+def _step(D, real, fake, B, dev, data_parallel, seed=77, sigma=2.0, C=1.5, overlap=False, fused=True):
     import csl_gan_b200 as cg
     D = copy.deepcopy(D).to(dev)
     opt = torch.optim.SGD(D.parameters(), lr=0.0)
     eng = cg.PrivacyEngine(D, batch_size=B, sample_size=60000, noise_multiplier=sigma, max_grad_norm=C,
                            num_private_passes=1, auto_clip_and_accum_on_step=False, data_parallel=data_parallel,
-                           overlap_allreduce=overlap)
+                           overlap_allreduce=overlap, fused_allreduce=fused)
     eng.attach(opt)
     eng._set_seed(seed)
     (D.real_loss(D(real.to(dev))[0]) + D.fake_loss(D(fake.to(dev))[0])).backward()
@@ -49,6 +49,15 @@ def _worker(rank, world, port, B, ret):
     both = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(both, flat)
     identical = all(torch.equal(both[0], b) for b in both[1:])
+    # default route on an NVSwitch box: the exchange and the noise in ONE kernel over peer-mapped symmetric memory
+    # (cg_noise_finalize_allreduce); it must give what the NCCL allreduce + noise kernel give (same Philox counters,
+    # the sum formed in rank order instead of NCCL's)
+    from csl_gan_b200.dist import SymmetricFlat
+    if SymmetricFlat.available():
+        assert eng._symm is not None, getattr(eng, "_symm_error", "symmetric memory not set up")
+        grads_n, eng_n = _step(D, real[lo:hi], fake[lo:hi], hi - lo, f"cuda:{rank}", True, fused=False)
+        assert eng_n._symm is None
+        identical = identical and all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(grads, grads_n))
     # the bucketed, overlapped allreduce (clip() reduces finished layers while the others are still contracting) gives
     # the same gradients as the single allreduce in step()
     grads_o, eng_o = _step(D, real[lo:hi], fake[lo:hi], hi - lo, f"cuda:{rank}", True, overlap=True)
