@@ -76,6 +76,14 @@ class ContractDesc(C.Structure):
     ]
 
 
+OP_ROW_SUMSQ, OP_COPY, OP_MUL, OP_WCOLSUM, OP_CLIP_MULT = 0, 1, 2, 3, 4
+
+
+class SmallOp(C.Structure):
+    _fields_ = [("op", C.c_int), ("R", C.c_int), ("lo", C.c_int), ("n", C.c_longlong), ("a", C.c_void_p), ("b", C.c_void_p),
+                ("c", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
+
+
 class NoiseSeg(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_longlong), ("std_mult", C.c_double),
                 ("std_dev", C.c_void_p)]
@@ -109,6 +117,7 @@ _PROTOS = {
     "cg_stage_yt_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                 C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_small_ops": (C.c_int, [C.POINTER(SmallOp), C.c_int, C.c_void_p]),
     "cg_thin_direct_ok": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int]),
     "cg_thin_capture": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p,
                                   C.c_int, C.POINTER(UnfoldGeom), C.c_int, C.c_float, C.c_void_p, C.c_longlong,
@@ -258,6 +267,22 @@ def noise_multi_allreduce(segs, mean: bool, seed, offset, offset_dev, local_flat
          C.byref(inc), local_flat.data_ptr(), int(mc_ptr) or None, peers, local_flat.numel(), int(count_off), int(rank),
          int(world), stream)
     return inc.value
+
+
+def small_op(op: int, a, out, n: int, b=None, c=None, out2=None, R: int = 0, lo: int = 0):
+    """One entry of a cg_small_ops table; tensors (or None), kept alive by the caller until the launch."""
+    return (op, R, lo, n, a, b, c, out, out2)
+
+
+def small_ops(ops, stream):
+    """Launch a table of small operations (see include/cslgan_b200.h cg_small_ops) in batches of 32."""
+    for i in range(0, len(ops), 32):
+        chunk = ops[i:i + 32]
+        arr = (SmallOp * len(chunk))()
+        for j, (op, R, lo, n, a, b, c, out, out2) in enumerate(chunk):
+            arr[j].op, arr[j].R, arr[j].lo, arr[j].n = op, int(R), int(lo), int(n)
+            arr[j].a, arr[j].b, arr[j].c, arr[j].out, arr[j].out2 = ptr(a), ptr(b), ptr(c), ptr(out), ptr(out2)
+        call("cg_small_ops", arr, len(chunk), stream)
 
 
 def cl_pair_ok(M: int, geom, plan) -> bool:

@@ -222,11 +222,16 @@ class ClLayerPlan:
             d.half, d.inv_x, d.inv_y = 1, L.ptr(self.inv_x), L.ptr(self.inv_y)
         return d
 
-    def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
+    def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1, ops=None):
+        """`ops`: a list that collects the small operations of this phase for ONE cg_small_ops launch (None: launch
+        them here)."""
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
         if self.kind == "linear":
             if n_joint == 1:
+                if ops is not None:
+                    ops.append(L.small_op(L.OP_MUL, self.asq[slot0:], norm2_row[slot0:], B, b=self.bsq[slot0:]))
+                    return
                 L.call("cg_vec_mul", L.ptr(self.asq[slot0:]), L.ptr(self.bsq[slot0:]), L.ptr(norm2_row[slot0:]), B, st)
                 return
             # ||sum_p b_p a_p^T||_F^2 = sum_{p,p'} (a_p . a_p') (b_p . b_p')
@@ -260,8 +265,11 @@ class ClLayerPlan:
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
         d.n_seg, d.seg_stride = n_joint, self.Bpad
         if self.direct:
-            norm2_row[slot0:slot0 + B].copy_(self.gnorm2[slot0:slot0 + B])
             self._gs_joint = 1
+            if ops is not None:
+                ops.append(L.small_op(L.OP_COPY, self.gnorm2[slot0:], norm2_row[slot0:], B))
+                return
+            norm2_row[slot0:slot0 + B].copy_(self.gnorm2[slot0:slot0 + B])
             return
         if self.thin:
             # G[slot][m][tap][c'] once (joint mode: the per-sample sum over passes lands in pass 0's slots);
@@ -275,9 +283,15 @@ class ClLayerPlan:
         d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
         L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
 
-    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
+    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1, ops=None):
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
+        if ops is not None and n_joint == 1:
+            if self.kind == "linear":
+                ops.append(L.small_op(L.OP_COPY, self.bsq[slot0:], norm2_row[slot0:], B))
+            else:
+                ops.append(L.small_op(L.OP_ROW_SUMSQ, self.bias_rows[slot0:], norm2_row[slot0:], B, R=self.bias_rows.shape[1]))
+            return
         if n_joint > 1:
             R = self.bias_rows.shape[1]
             L.call("cg_joint_rows_sumsq", L.ptr(self.bias_rows), R, slot0, self.Bpad, n_joint, B,
@@ -289,7 +303,16 @@ class ClLayerPlan:
         R = self.bias_rows.shape[1]
         L.call("cg_row_sumsq", L.ptr(self.bias_rows[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
 
-    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0):
+    def clip_mult_op(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
+        """The clip-multiplier computation of scale_backprops() as a cg_small_ops entry (None when this layer has
+        none: thin layers, TF32 operands, more than 65536 slots); scale_backprops(mult_ready=True) then skips it."""
+        if self.thin or not self.half or slot_hi - slot_lo > 65536:
+            return None
+        return L.small_op(L.OP_CLIP_MULT, factor_row, self.mult, slot_hi - slot_lo, b=self.inv_x, c=self.inv_y,
+                          out2=self.out_scale, lo=slot_lo)
+
+    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0,
+                        mult_ready: bool = False):
         """Xc = tf32(Xt * factor[slot - factor_shift]): every chunk of Xt is a row of slot-sized (Q*32) segments.
         factor_shift != 0 reuses pass 0's (joint) factors for a later pass."""
         if self.thin:
@@ -299,8 +322,9 @@ class ClLayerPlan:
             if factor_shift:
                 raise L.CslGanCudaError(f"{self.name}: joint clipping needs TF32 operands")
             st = L.stream_ptr(factor_row.device)
-            L.call("cg_clip_mult", L.ptr(factor_row), L.ptr(self.inv_x), L.ptr(self.inv_y), slot_lo, slot_hi,
-                   L.ptr(self.mult), L.ptr(self.out_scale), st)
+            if not mult_ready:
+                L.call("cg_clip_mult", L.ptr(factor_row), L.ptr(self.inv_x), L.ptr(self.inv_y), slot_lo, slot_hi,
+                       L.ptr(self.mult), L.ptr(self.out_scale), st)
             L.call("cg_scale_slots_h", L.ptr(self.Xt), L.ptr(self.Xc), self.x_chunks, self.x_rows * self.cw,
                    self.Q * self.cw, slot_lo, slot_hi, L.ptr(self.mult), st)
             return
@@ -308,10 +332,12 @@ class ClLayerPlan:
                slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, L.stream_ptr(factor_row.device))
 
     def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool,
-                     factor_row: Optional[torch.Tensor] = None):
+                     factor_row: Optional[torch.Tensor] = None, prezeroed: bool = False, ops=None):
+        """`prezeroed`: out_w already holds zeros (the engine clears the whole flat buffer once per step).
+        `ops`: thin layers append their weighted column sum to this cg_small_ops table instead of launching it."""
         st = L.stream_ptr(out_w.device)
         if self.thin:
-            return self._thin_weighted_sum(out_w, slot_lo, slot_hi, accumulate, factor_row, st)
+            return self._thin_weighted_sum(out_w, slot_lo, slot_hi, accumulate, factor_row, st, prezeroed, ops)
         d = self._desc(self.Xc)
         # tiles per K range (mirror of cg_cl_contract) -> split K so the grid covers the machine ~2x
         n_cb, n_taps = self.n_cb, self.plan.n_taps
@@ -348,7 +374,7 @@ class ClLayerPlan:
             # channels_last weight memory is [m][kh][kw][c] = T[m][tap][c'] (merged: c' = kw*C + c)
             natural = out_w.permute(0, 2, 3, 1)
         target = natural if natural is not None else self.T
-        if target is self.T or not accumulate:
+        if target is self.T or not (accumulate or prezeroed):
             target.zero_()
         d.epi, d.out, d.out_group_stride = L.EPI_ACCUM, L.ptr(target), 0
         L.call("cg_cl_contract", C.byref(d), C.byref(self.geom), C.byref(self.plan), st)
@@ -364,7 +390,7 @@ class ClLayerPlan:
             if dst is not out_w:
                 out_w.add_(dst) if accumulate else out_w.copy_(dst)
 
-    def _thin_weighted_sum(self, out_w, slot_lo, slot_hi, accumulate, factor_row, st):
+    def _thin_weighted_sum(self, out_w, slot_lo, slot_hi, accumulate, factor_row, st, prezeroed=False, ops=None):
         """sum_slot factor[slot] * G[slot] over the materialised per-sample gradients (natural layout)."""
         if factor_row is None:
             raise L.CslGanCudaError(f"{self.name}: the thin-layer path needs the clip factors")
@@ -376,8 +402,11 @@ class ClLayerPlan:
                 and out_w.is_contiguous(memory_format=torch.channels_last)):
             natural = out_w.permute(0, 2, 3, 1)               # [m][kh][kw][c] == T[m][tap][c'] (merged or not)
         target = natural if natural is not None else self.T
+        if ops is not None and natural is not None and (accumulate or prezeroed):
+            ops.append(L.small_op(L.OP_WCOLSUM, self.Gs, target, slot_hi - slot_lo, b=factor_row, R=R, lo=slot_lo))
+            return
         L.call("cg_weighted_colsum", L.ptr(self.Gs), L.ptr(factor_row), slot_lo, slot_hi, R, L.ptr(target),
-               1 if (accumulate and natural is not None) else 0, st)
+               1 if ((accumulate or prezeroed) and natural is not None) else 0, st)
         if natural is None:
             if not out_w.is_contiguous():
                 raise L.CslGanCudaError(f"{self.name}: unsupported weight memory layout {out_w.stride()}")
@@ -385,8 +414,11 @@ class ClLayerPlan:
                    1 if accumulate else 0, st)
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
-                          accumulate: bool, factor_shift: int = 0):
+                          accumulate: bool, factor_shift: int = 0, ops=None):
         R = self.bias_rows.shape[1]
+        if ops is not None and factor_shift == 0 and accumulate:
+            ops.append(L.small_op(L.OP_WCOLSUM, self.bias_rows, out_b, slot_hi - slot_lo, b=factor_row, R=R, lo=slot_lo))
+            return
         L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row) - 4 * factor_shift, slot_lo, slot_hi, R,
                L.ptr(out_b), 1 if accumulate else 0, L.stream_ptr(out_b.device))
 

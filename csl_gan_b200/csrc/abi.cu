@@ -1309,6 +1309,55 @@ int cg_weighted_colsum(const float* rows_in, const float* factor, int slot_lo, i
   return 0;
 }
 
+int cg_small_ops(const cg_small_op* ops, int n_ops, cg_stream_t stream) {
+  if (n_ops <= 0) return 0;
+  if (!ops) return fail("null operation table");
+  if (n_ops > cg::kSmallMaxOps) return fail("at most %d operations per cg_small_ops call", cg::kSmallMaxOps);
+  cg::SmallParams p;
+  memset(&p, 0, sizeof(p));
+  int blk = 0, m = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const cg_small_op& in = ops[i];
+    if (in.n <= 0) continue;
+    if (!in.a || !in.out) return fail("operation %d: null operand", i);
+    cg::SmallOp& o = p.op[m];
+    o.op = in.op; o.R = in.R; o.lo = in.lo; o.n = in.n; o.a = in.a; o.b = in.b; o.c = in.c; o.out = in.out; o.out2 = in.out2;
+    o.blk0 = blk; o.nx = 1;
+    long long nb = 1;
+    switch (in.op) {
+      case CG_OP_ROW_SUMSQ:
+        if (in.R <= 0) return fail("operation %d: R must be positive", i);
+        nb = (in.n + 7) / 8; if (nb > 256) nb = 256; break;
+      case CG_OP_MUL:
+        if (!in.b) return fail("operation %d: null operand", i);
+        // fall through
+      case CG_OP_COPY:
+        nb = (in.n + 255) / 256; if (nb > 64) nb = 64; break;
+      case CG_OP_WCOLSUM: {
+        if (!in.b || in.R <= 0) return fail("operation %d: bad weighted column sum", i);
+        if (in.lo + in.n > 0x7fffffffLL) return fail("operation %d: slot range too large", i);
+        o.nx = (in.R + 31) / 32;
+        long long ny = (in.n + 31) / 32; if (ny > 128) ny = 128; if (ny < 1) ny = 1;
+        nb = static_cast<long long>(o.nx) * ny; break;
+      }
+      case CG_OP_CLIP_MULT:
+        if (!in.b || !in.c || !in.out2) return fail("operation %d: null operand", i);
+        if (in.n > 65536) return fail("operation %d: more than 65536 slots (use cg_clip_mult)", i);
+        nb = 1; break;
+      default:
+        return fail("operation %d: unknown op %d", i, in.op);
+    }
+    o.nblk = static_cast<int>(nb);
+    blk += o.nblk;
+    ++m;
+  }
+  if (m == 0) return 0;
+  p.n_ops = m;
+  cg::small_ops_kernel<<<blk, 256, 0, S(stream)>>>(p);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
 int cg_row_stat(const float* norms, int n_rows, int n_slots, int slot_lo, int slot_hi, int stat, float scalar,
                 float* out, cg_stream_t stream) {
   if (n_rows <= 0) return 0;

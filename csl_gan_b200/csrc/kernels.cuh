@@ -406,6 +406,100 @@ __global__ void weighted_colsum_kernel(const float* __restrict__ rows_in, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched small operations: the per-layer scalar / bias work of a step (bias-gradient norms, Linear closed-form
+// norms, clip multipliers, bias and thin-layer clipped sums) is ~25 launches of 3-5 us each when issued one by one --
+// 8 % of the CelebA step.  One launch runs a table of them; a block finds its operation by the table's block prefix.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallMaxOps = 32;
+struct SmallOp {
+  int op;                      // CG_OP_*
+  int R;                       // columns (ROW_SUMSQ, WCOLSUM)
+  int lo;                      // first slot (WCOLSUM, CLIP_MULT)
+  int blk0;                    // first block of this operation
+  int nblk;                    // blocks of this operation
+  int nx;                      // WCOLSUM: column tiles of 32
+  long long n;                 // rows / elements / slots
+  const float* a;
+  const float* b;
+  const float* c;
+  float* out;
+  float* out2;
+};
+struct SmallParams {
+  SmallOp op[kSmallMaxOps];
+  int n_ops;
+};
+
+__global__ void __launch_bounds__(256)
+small_ops_kernel(const __grid_constant__ SmallParams p) {
+  __shared__ float red[8][33];
+  __shared__ float s_down;
+  int i = 0;
+#pragma unroll 1
+  while (i + 1 < p.n_ops && static_cast<int>(blockIdx.x) >= p.op[i + 1].blk0) ++i;
+  const SmallOp& o = p.op[i];
+  const int bl = blockIdx.x - o.blk0;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (o.op == CG_OP_ROW_SUMSQ) {
+    // out[r] = sum_j a[r*R + j]^2 : one warp per row
+    for (long long r = static_cast<long long>(bl) * 8 + w; r < o.n; r += static_cast<long long>(o.nblk) * 8) {
+      const float* row = o.a + r * o.R;
+      float acc = 0.f;
+      for (int j = lane; j < o.R; j += 32) acc = fmaf(row[j], row[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) o.out[r] = acc;
+    }
+  } else if (o.op == CG_OP_COPY || o.op == CG_OP_MUL) {
+    for (long long j = static_cast<long long>(bl) * 256 + t; j < o.n; j += static_cast<long long>(o.nblk) * 256)
+      o.out[j] = o.op == CG_OP_COPY ? o.a[j] : o.a[j] * o.b[j];
+  } else if (o.op == CG_OP_WCOLSUM) {
+    // out[r] += sum_s b[lo + s] * a[(lo + s)*R + r]  (out zeroed by the caller); 32 columns x 8 slot lanes per block
+    const int tx = t & 31, ty = t >> 5;
+    const int ct = bl % o.nx, sy = bl / o.nx, ny = o.nblk / o.nx;
+    const int r = ct * 32 + tx;
+    const int per = static_cast<int>((o.n + ny - 1) / ny);
+    const int s0 = o.lo + sy * per;
+    const int s1 = min(s0 + per, o.lo + static_cast<int>(o.n));
+    float acc = 0.f;
+    if (r < o.R)
+      for (int s = s0 + ty; s < s1; s += 8) acc = fmaf(__ldg(o.b + s), __ldg(o.a + static_cast<long long>(s) * o.R + r), acc);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && r < o.R) {
+#pragma unroll
+      for (int k = 1; k < 8; ++k) acc += red[k][tx];
+      if (s1 > s0) atomicAdd(o.out + r, acc);
+    }
+  } else if (o.op == CG_OP_CLIP_MULT) {
+    // out[s] = a[s]*b[s]*c[s] / 2^E, out2[0] = 2^E (cl.cuh clip_mult_kernel for one layer, one block)
+    const int hi = o.lo + static_cast<int>(o.n);
+    float m = 0.f;
+    for (int s = o.lo + t; s < hi; s += 256) m = fmaxf(m, o.a[s] * o.b[s] * o.c[s]);
+    m = warp_max(m);
+    if (lane == 0) red[0][w] = m;
+    __syncthreads();
+    if (w == 0) {
+      m = lane < 8 ? red[0][lane] : 0.f;
+      m = warp_max(m);
+      if (lane == 0) {
+        float up = 1.f;
+        if (m > 0.f && isfinite(m)) {
+          int e;
+          frexpf(m, &e);
+          e = e > 126 ? 126 : (e < -126 ? -126 : e);
+          up = __int_as_float((e + 127) << 23);
+        }
+        o.out2[0] = up;
+        s_down = 1.0f / up;
+      }
+    }
+    __syncthreads();
+    const float down = s_down;
+    for (int s = o.lo + t; s < hi; s += 256) o.out[s] = o.a[s] * o.b[s] * o.c[s] * down;
+  }
+}
+
 __global__ void row_stat_kernel(const float* __restrict__ norms, int n_rows, int n_slots, int slot_lo, int slot_hi,
                                 int stat, float scalar, float* __restrict__ out) {
   __shared__ float sh[32];

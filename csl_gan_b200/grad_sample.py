@@ -215,10 +215,11 @@ class LayerPlan:
         d.max_ctas = 0
         return d
 
-    def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
-        """norm2_row[slot] += ||G_slot||_F^2 for the slots of one pass."""
+    def weight_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1, ops=None):
+        """norm2_row[slot] += ||G_slot||_F^2 for the slots of one pass.  `ops` (channels-last plans): collect the
+        small launches of this phase into one cg_small_ops table instead of issuing them."""
         if self.impl is not None:
-            return self.impl.weight_norm2(norm2_row, pass_idx, B, n_joint)
+            return self.impl.weight_norm2(norm2_row, pass_idx, B, n_joint, ops)
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
         if self.kind == "linear":
@@ -233,9 +234,9 @@ class LayerPlan:
         d.epi, d.out, d.out_group_stride = L.EPI_SUMSQ, L.ptr(norm2_row[slot0:]), 0
         L.call("cg_contract", C.byref(d), st)
 
-    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1):
+    def bias_norm2(self, norm2_row: torch.Tensor, pass_idx: int, B: int, n_joint: int = 1, ops=None):
         if self.impl is not None:
-            return self.impl.bias_norm2(norm2_row, pass_idx, B, n_joint)
+            return self.impl.bias_norm2(norm2_row, pass_idx, B, n_joint, ops)
         slot0 = pass_idx * self.Bpad
         st = L.stream_ptr(norm2_row.device)
         if n_joint > 1:
@@ -250,20 +251,30 @@ class LayerPlan:
         R = self.bias_rows.shape[1]
         L.call("cg_row_sumsq", L.ptr(self.bias_rows[slot0:]), B, R, R, L.ptr(norm2_row[slot0:]), 0, st)
 
-    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0):
+    def clip_mult_op(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int):
+        """cg_small_ops entry that prepares scale_backprops(mult_ready=True), or None."""
+        if self.impl is not None:
+            return self.impl.clip_mult_op(factor_row, slot_lo, slot_hi)
+        return None
+
+    def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0,
+                        mult_ready: bool = False):
         """Xc = tf32(X * factor[slot - factor_shift]) over the slot range (clip factors folded into one operand)."""
         if self.impl is not None:
-            return self.impl.scale_backprops(factor_row, slot_lo, slot_hi, factor_shift)
+            return self.impl.scale_backprops(factor_row, slot_lo, slot_hi, factor_shift, mult_ready)
         st = L.stream_ptr(factor_row.device)
         L.call("cg_scale_slots", L.ptr(self.X), L.ptr(self.Xc), self.M, self.X.stride(0), self.x_slot_stride,
                slot_lo, slot_hi, L.ptr(factor_row) - 4 * factor_shift, st)
 
     def weighted_sum(self, out_w: torch.Tensor, slot_lo: int, slot_hi: int, sm_count: int, accumulate: bool,
-                     factor_row: Optional[torch.Tensor] = None):
+                     factor_row: Optional[torch.Tensor] = None, prezeroed: bool = False, ops=None):
         """out_w (+)= sum_slot Xc[:, slot] (x) Y[:, slot]: ONE split-K GEMM over all slots (factor_row is only
-        used by the thin-layer path of the channels-last plan, which sums materialised per-sample gradients)."""
+        used by the thin-layer path of the channels-last plan, which sums materialised per-sample gradients).
+        `prezeroed`: out_w already holds zeros; `ops`: see ClLayerPlan.weighted_sum."""
         if self.impl is not None:
-            return self.impl.weighted_sum(out_w, slot_lo, slot_hi, sm_count, accumulate, factor_row)
+            return self.impl.weighted_sum(out_w, slot_lo, slot_hi, sm_count, accumulate, factor_row, prezeroed, ops)
+        if prezeroed:
+            accumulate = True
         st = L.stream_ptr(out_w.device)
         d = self._desc(self.Xc)
         # mirror of the tile choice in cg_contract (csrc/abi.cu)
@@ -316,9 +327,9 @@ class LayerPlan:
                    1 if accumulate else 0, st)
 
     def bias_weighted_sum(self, out_b: torch.Tensor, factor_row: torch.Tensor, slot_lo: int, slot_hi: int,
-                          accumulate: bool, factor_shift: int = 0):
+                          accumulate: bool, factor_shift: int = 0, ops=None):
         if self.impl is not None:
-            return self.impl.bias_weighted_sum(out_b, factor_row, slot_lo, slot_hi, accumulate, factor_shift)
+            return self.impl.bias_weighted_sum(out_b, factor_row, slot_lo, slot_hi, accumulate, factor_shift, ops)
         st = L.stream_ptr(out_b.device)
         R = self.bias_rows.shape[1]
         L.call("cg_weighted_colsum", L.ptr(self.bias_rows), L.ptr(factor_row) - 4 * factor_shift, slot_lo, slot_hi, R,

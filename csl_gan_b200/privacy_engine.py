@@ -21,6 +21,8 @@ Fork semantics that cannot be verified here are explicit switches (SURVEY.md §8
 """
 from __future__ import annotations
 
+import os
+
 import math
 import types
 from itertools import cycle
@@ -231,6 +233,7 @@ class PrivacyEngine:
             self.operand_dtype = "tf32"
         self.overlap_allreduce = bool(overlap_allreduce)
         self.fused_allreduce = bool(fused_allreduce)
+        self.batch_small_ops = os.environ.get("CSLGAN_BATCH_SMALL", "1") != "0"
         self._symm = None
         self._symm_failed = False
         self._symm_last = 1
@@ -595,6 +598,7 @@ class PrivacyEngine:
         joint = n_passes if (self.accum_passes and n_passes > 1) else 1
         if joint > 1 and len({self._pass_B[ps] for ps in range(n_passes)}) != 1:
             raise RuntimeError("accum_passes=True needs the same batch size in every pass")
+        small = [] if self.batch_small_ops else None         # per-layer scalar work batched into one launch
         for plan in self._plans:
             live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
             if not live:
@@ -614,9 +618,11 @@ class PrivacyEngine:
             else:
                 spans = [(ps, self._pass_B[ps]) for ps in live]
             for ps, nb in spans:
-                plan.weight_norm2(self._norm2[plan.w_idx], ps, nb, 1)
+                plan.weight_norm2(self._norm2[plan.w_idx], ps, nb, 1, small)
                 if plan.b_idx is not None:
-                    plan.bias_norm2(self._norm2[plan.b_idx], ps, nb)
+                    plan.bias_norm2(self._norm2[plan.b_idx], ps, nb, 1, small)
+        if small:
+            L.small_ops(small, L.stream_ptr(self.device))     # bias norms, Linear closed forms: ONE launch
         self._norms_valid = True
         self._factors_valid = False
 
@@ -757,6 +763,18 @@ class PrivacyEngine:
                 flat[self._n_theta:].fill_(float(self._cur_B))
                 self._reduced_early = True
         sms = self._sm_count
+        st = L.stream_ptr(self.device)
+        joint = self.accum_passes and n_passes > 1
+        # the whole flat buffer is cleared ONCE (instead of one fill per layer), and the small per-layer launches that
+        # depend on the factors only -- clip multipliers, bias sums, thin-layer sums -- go into ONE cg_small_ops table
+        # ahead of the GEMMs.  Joint clipping and the overlapped allreduce keep the layer-by-layer order.
+        batched = self.batch_small_ops and not joint and buckets is None
+        if batched:
+            flat.zero_()
+            for o_, p_ in zip(outs, self._params):
+                if o_.data_ptr() < flat.data_ptr() or o_.data_ptr() >= flat.data_ptr() + flat.numel() * 4:
+                    o_.zero_()
+        todo = []
         for plan in plans:
             live = [ps for ps in range(self._pass_count.get(plan, 0)) if (plan, ps) in self._bp_seen]
             if not live:
@@ -764,7 +782,6 @@ class PrivacyEngine:
                 if plan.b_idx is not None:
                     outs[plan.b_idx].zero_()
                 continue
-            joint = self.accum_passes and n_passes > 1
             if joint:
                 # every pass is scaled with pass 0's (joint) factors
                 ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], ps * self.Bpad) for ps in live]
@@ -772,21 +789,46 @@ class PrivacyEngine:
                 ranges = [(0, slot_hi, 0)]
             else:
                 ranges = [(ps * self.Bpad, ps * self.Bpad + self._pass_B[ps], 0) for ps in live]
+            todo.append((plan, ranges))
+        small = [] if batched else None
+        ready = set()
+        if batched:
+            for plan, ranges in todo:
+                frow_w = self._factors[plan.w_idx if self._per_layer else 0]
+                if len(ranges) == 1:
+                    lo, hi, _ = ranges[0]
+                    op = plan.clip_mult_op(frow_w, lo, _round_up(hi, 32))
+                    if op is not None:
+                        small.append(op)
+                        ready.add(plan)
+                if plan.b_idx is not None:
+                    frow_b = self._factors[plan.b_idx if self._per_layer else 0]
+                    for lo, hi, shift in ranges:
+                        plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=True, factor_shift=shift, ops=small)
+                if getattr(plan.impl, "thin", False) and len(ranges) == 1:
+                    plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[0][1], sms, accumulate=False,
+                                      factor_row=frow_w, prezeroed=True, ops=small)
+                    ready.add(("thin", plan))
+            L.small_ops(small, st)
+        for plan, ranges in todo:
+            if ("thin", plan) in ready:
+                continue                                     # its clipped sum was one of the batched operations
             frow_w = self._factors[plan.w_idx if self._per_layer else 0]
             # scale up to the next 32-slot boundary (Bpad is a multiple of 32, dead slots have factor 0):
             # the contraction reads whole 32-row K blocks, which may reach past `hi` when Q < 32
             if joint or len(ranges) == 1:
                 for lo, hi, shift in ranges:
-                    plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
+                    plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift, mult_ready=plan in ready)
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
                 plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], sms, accumulate=False,
-                                  factor_row=frow_w)
+                                  factor_row=frow_w, prezeroed=batched)
             else:
                 # range by range: with FP16 operands every scale_backprops() call has its own common scale
                 for i, (lo, hi, shift) in enumerate(ranges):
                     plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift)
-                    plan.weighted_sum(outs[plan.w_idx], lo, hi, sms, accumulate=i > 0, factor_row=frow_w)
-            if plan.b_idx is not None:
+                    plan.weighted_sum(outs[plan.w_idx], lo, hi, sms, accumulate=i > 0, factor_row=frow_w,
+                                      prezeroed=batched and i == 0)
+            if plan.b_idx is not None and not batched:
                 frow_b = self._factors[plan.b_idx if self._per_layer else 0]
                 for i, (lo, hi, shift) in enumerate(ranges):
                     plan.bias_weighted_sum(outs[plan.b_idx], frow_b, lo, hi, accumulate=i > 0, factor_shift=shift)

@@ -236,6 +236,28 @@ int cg_stage_xt_h(const float* src, long long sn, long long sm, long long sh, lo
 int cg_stage_yt_h(const float* src, long long sn, long long sc, long long sh, long long sw, int B,
                   const cg_unfold_geom* g, const cg_cl_plan* plan, float scale, void* dst_half, int n_slots_total,
                   int slot0, unsigned int* amax, float* inv, cg_stream_t stream);
+/* Batched small operations: ONE launch for a table of the per-layer scalar / bias operations of a step (each is a
+ * 3-5 us launch on its own; a CelebA step has ~25 of them).  Same arithmetic as the single-operation entry points:
+ *   CG_OP_ROW_SUMSQ  out[r] = sum_j a[r*R + j]^2, r < n                      (cg_row_sumsq; bias-gradient norms)
+ *   CG_OP_COPY       out[j] = a[j], j < n
+ *   CG_OP_MUL        out[j] = a[j] * b[j], j < n                            (cg_vec_mul; Linear closed-form norms)
+ *   CG_OP_WCOLSUM    out[r] += sum_{s in [lo, lo+n)} b[s] * a[s*R + r]      (cg_weighted_colsum, out zeroed by the caller)
+ *   CG_OP_CLIP_MULT  out[s] = a[s]*b[s]*c[s] / 2^E, out2[0] = 2^E, s in [lo, lo+n), n <= 65536   (cg_clip_mult)
+ * At most 32 operations per call. */
+enum { CG_OP_ROW_SUMSQ = 0, CG_OP_COPY = 1, CG_OP_MUL = 2, CG_OP_WCOLSUM = 3, CG_OP_CLIP_MULT = 4 };
+typedef struct {
+  int op;
+  int R;
+  int lo;
+  long long n;
+  const float* a;
+  const float* b;
+  const float* c;
+  float* out;
+  float* out2;
+} cg_small_op;
+int cg_small_ops(const cg_small_op* ops, int n_ops, cg_stream_t stream);
+
 /* Thin first convolution (few input channels, large window grid: the 3 -> 64 channel conv of the CelebA critics):
  * per-sample weight gradients, their squared norms and the per-sample bias gradients in ONE kernel that reads the
  * layer's own tensors -- no staged operands (csrc/thin.cuh).  Replaces, for such a layer, the fork's
