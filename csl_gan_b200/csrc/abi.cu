@@ -16,6 +16,7 @@
 #include "cl_pair.cuh"
 #include "stage2.cuh"
 #include "thin.cuh"
+#include "cl_res.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -1089,6 +1090,74 @@ int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan) {
   return (M >= 256 && M % 256 == 0 && plan->Cp >= 128 && plan->Cp % 128 == 0 && !plan->merged) ? 1 : 0;
 }
 
+// Per-sample norms with the sample's backprops resident in shared memory and the taps read as shifted windows of one
+// plane box (cl_res.cuh).  Returns 0 = launched, 1 = geometry not covered (caller falls back), -1 = error.
+static int res_mode() {
+  // CSLGAN_RESIDENT: 0 = off; otherwise the flags of cl_res.cuh + 4 (bit 0: descriptor base offset, bit 1: one MMA
+  // per tap); default on with the combination validated on B200
+  static const int m = [] { const char* e = getenv("CSLGAN_RESIDENT"); return e ? atoi(e) : 4; }();
+  return m;
+}
+
+int launch_resident_norm(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, int sm_count,
+                         cg_stream_t stream) {
+  const int mode = res_mode();
+  if (!(mode & 4)) return 1;
+  const int Q = g->Ho * g->Wo;
+  if (!d->half || plan->merged || plan->cw != 64 || plan->Cp != 64 || d->M > 128 || (g->Wo != 16 && g->Wo != 32 && g->Wo != 64) ||
+      Q % 64 || static_cast<long long>(Q) * 256 > cg::kResXBytes || (d->n_seg > 1))
+    return 1;
+  cg::ResParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.Q = Q; p.Wo = g->Wo; p.Ws = plan->Ws; p.nkb = Q / 64; p.kb_h = 64 / g->Wo; p.n_cb = 1;
+  p.y_bytes = 128 * plan->Ws * p.kb_h;
+  if (p.y_bytes > cg::kResYStride) return 1;
+  // tiles: taps grouped by (plane, row shift), column shifts consecutive
+  const int n_taps = plan->n_taps;
+  bool used[CG_MAX_KH * CG_MAX_KH] = {false};
+  for (int t = 0; t < n_taps; ++t) {
+    if (used[t]) continue;
+    int lo = plan->tap_woff[t], hi = lo;
+    for (int u = 0; u < n_taps; ++u)
+      if (plan->tap_plane[u] == plan->tap_plane[t] && plan->tap_hoff[u] == plan->tap_hoff[t]) {
+        used[u] = true;
+        if (plan->tap_woff[u] < lo) lo = plan->tap_woff[u];
+        if (plan->tap_woff[u] > hi) hi = plan->tap_woff[u];
+      }
+    int cnt = 0;
+    for (int u = 0; u < n_taps; ++u)
+      if (plan->tap_plane[u] == plan->tap_plane[t] && plan->tap_hoff[u] == plan->tap_hoff[t]) ++cnt;
+    if (cnt != hi - lo + 1 || cnt > 4 || p.n_tiles >= cg::kResMaxTiles) return 1;     // shifts must be consecutive
+    p.tile_plane[p.n_tiles] = plan->tap_plane[t]; p.tile_hoff[p.n_tiles] = plan->tap_hoff[t];
+    p.tile_woff[p.n_tiles] = lo; p.tile_ndw[p.n_tiles] = cnt;
+    ++p.n_tiles;
+  }
+  // the last slab of a k-block must end inside the plane box
+  for (int t = 0; t < p.n_tiles; ++t) {
+    const int last = (p.kb_h - 1) * plan->Ws + (g->Wo - 16) + p.tile_woff[t] + p.tile_ndw[t] - 1 + 15;
+    if (last >= plan->Ws * p.kb_h) return 1;
+  }
+  p.slot_lo = d->slot_lo; p.n_groups = d->n_groups; p.out = d->out; p.inv_x = d->inv_x; p.inv_y = d->inv_y;
+  p.flags = mode & 3;
+  CUtensorMap tx, ty;
+  if (make_cl_tmaps(&tx, &ty, d, plan, 1, 64, plan->Ws, p.kb_h, 1, 1)) return -1;
+  const int smem = 1024 + 2 * cg::kResXBytes + cg::kResYStages * cg::kResYStride + 512;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { fail("cudaGetDevice failed"); return -1; }
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(cg::cl_resident_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      fail("cl_resident_norm_kernel: shared memory attribute"); return -1;
+    }
+    attr_set[dev] = true;
+  }
+  long long grid = d->max_ctas > 0 ? d->max_ctas : sm_count;
+  if (grid > p.n_groups) grid = p.n_groups;
+  cg::cl_resident_norm_kernel<<<static_cast<int>(grid), cg::kClThreads, smem, S(stream)>>>(tx, ty, p);
+  if (cudaGetLastError() != cudaSuccess) { fail("cl_resident_norm_kernel launch failed"); return -1; }
+  return 0;
+}
+
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream) {
   if (!d || !g || !plan) return fail("null argument");
   DevInfo dv;
@@ -1096,6 +1165,11 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   if (dv.major != 10) return fail("cg_cl_contract needs an sm_100-class device (found sm_%d%d)", dv.major, dv.minor);
   if (d->n_groups <= 0) return 0;
   const int Q = g->Ho * g->Wo;
+  if (d->half && d->group_mode == CG_GROUP_SAMPLE && d->epi == CG_EPI_SUMSQ && !d->pair && d->inv_x && d->inv_y) {
+    const int rc = launch_resident_norm(d, g, plan, dv.sm, stream);
+    if (rc == 0) return 0;
+    if (rc < 0) return 1;
+  }
   int kb_rows, kb_w, kb_h, kb_s;
   if (cl_kblock(g, d->group_mode == CG_GROUP_SAMPLE, &kb_rows, &kb_w, &kb_h, &kb_s, d->half)) return 1;
   cg::ClParams p;

@@ -314,13 +314,8 @@ cl_contract_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
 
       if (p.epi == CG_EPI_SUMSQ) {
         // rows >= M and channels >= C were zero-filled by TMA: no masking needed
-        float ss = 0.f;
-        for (int c0 = 0; c0 < Cfg::kCW * nbv; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) ss = fmaf(v[j], v[j], ss);
-        }
+        const float ss0 = tmem_sumsq(taddr, Cfg::kCW * nbv, 0.f);       // (kCW * nbv is a multiple of 32)
+        float ss = ss0;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);

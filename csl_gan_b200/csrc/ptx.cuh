@@ -132,6 +132,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread, WITHOUT the wait: several loads can be in flight
+// before one tmem_wait_ld() (the per-load wait of tmem_ld16 serialises a TMEM round trip per 16 columns, which is what
+// bounded the per-sample norm epilogues: 100 round trips per sample of the 16x16 CelebA layer)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// sum of squares of `ncol` (a multiple of 32) accumulator columns of this warp's 32 lanes, two 32-column loads in
+// flight per wait
+__device__ __forceinline__ float tmem_sumsq(uint32_t taddr, int ncol, float ss) {
+  int c0 = 0;
+  for (; c0 + 64 <= ncol; c0 += 64) {
+    uint32_t a[32], b[32];
+    tmem_ld32_nowait(taddr + c0, a);
+    tmem_ld32_nowait(taddr + c0 + 32, b);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]); ss = fmaf(x, x, ss); }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(b[j]); ss = fmaf(x, x, ss); }
+  }
+  for (; c0 < ncol; c0 += 32) {
+    uint32_t a[32];
+    tmem_ld32_nowait(taddr + c0, a);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(a[j]); ss = fmaf(x, x, ss); }
+  }
+  return ss;
+}
+
 // ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ---------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
