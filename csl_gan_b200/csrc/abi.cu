@@ -1105,11 +1105,11 @@ int launch_resident_norm(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_
   if (!(mode & 4)) return 1;
   const int Q = g->Ho * g->Wo;
   if (!d->half || plan->merged || plan->cw != 64 || plan->Cp != 64 || d->M > 128 || (g->Wo != 16 && g->Wo != 32 && g->Wo != 64) ||
-      Q % 64 || static_cast<long long>(Q) * 256 > cg::kResXBytes || (d->n_seg > 1))
+      Q % cg::kResKb || static_cast<long long>(Q) * 256 > cg::kResXBytes || (d->n_seg > 1))
     return 1;
   cg::ResParams p;
   memset(&p, 0, sizeof(p));
-  p.M = d->M; p.Q = Q; p.Wo = g->Wo; p.Ws = plan->Ws; p.nkb = Q / 64; p.kb_h = 64 / g->Wo; p.n_cb = 1;
+  p.M = d->M; p.Q = Q; p.Wo = g->Wo; p.Ws = plan->Ws; p.nkb = Q / cg::kResKb; p.kb_h = cg::kResKb / g->Wo; p.n_cb = 1;
   p.y_bytes = 128 * plan->Ws * p.kb_h;
   if (p.y_bytes > cg::kResYStride) return 1;
   // tiles: taps grouped by (plane, row shift), column shifts consecutive

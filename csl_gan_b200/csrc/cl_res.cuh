@@ -18,15 +18,17 @@
 
 namespace cg {
 
-constexpr int kResYStages = 8;
+constexpr int kResYStages = 4;
 constexpr int kResMaxTiles = 32;
 constexpr int kResXBytes = 64 * 1024;                // resident backprops of one sample (two buffers)
-constexpr int kResYStride = 10 * 1024;               // one plane box (<= 80 rows of 128 B), 1024-byte aligned
+constexpr int kResYStride = 20 * 1024;               // one plane box (<= 160 rows of 128 B), 1024-byte aligned
+constexpr int kResKb = 128;                          // window positions per k-block: 8 MMAs per barrier round trip (with 4
+                                                     // the issuing thread, not the tensor pipe, set the pace: 52 % active)
 
 struct ResParams {
   int M, Q, Wo, Ws;
-  int nkb;                     // 64-position k-blocks per sample
-  int kb_h;                    // window rows per k-block (64 / Wo)
+  int nkb;                     // 128-position k-blocks per sample
+  int kb_h;                    // window rows per k-block (128 / Wo)
   int n_tiles;
   int tile_plane[kResMaxTiles], tile_hoff[kResMaxTiles], tile_woff[kResMaxTiles], tile_ndw[kResMaxTiles];
   int slot_lo, n_groups;
@@ -76,8 +78,9 @@ cl_resident_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __gri
       for (int g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
         const int slot = p.slot_lo + g;
         mbar_wait(&x_empty[xb], xph ^ 1);
-        mbar_expect_tx(&x_full[xb], static_cast<uint32_t>(p.nkb * x_kb_bytes));
-        for (int kb = 0; kb < p.nkb; ++kb)
+        const int n_xbox = p.Q / 64;
+        mbar_expect_tx(&x_full[xb], static_cast<uint32_t>(n_xbox * x_kb_bytes));
+        for (int kb = 0; kb < n_xbox; ++kb)
           tma_load_3d(xs + xb * kResXBytes + kb * x_kb_bytes, &tmap_xt, &x_full[xb], 0, slot * p.Q + kb * 64, 0);
         if (++xb == 2) { xb = 0; xph ^= 1; }
         for (int t = 0; t < p.n_tiles; ++t) {
@@ -97,9 +100,9 @@ cl_resident_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __gri
       // does not change per k-block is hoisted -- slab rows (the only divisions), descriptor templates (a descriptor
       // is additive in its start address: +8 per 128-byte row), instruction descriptors per tile.
       int xb = 0; uint32_t xph = 0; int st = 0; uint32_t yph = 0; int acc = 0; uint32_t aph = 0;
-      uint32_t slab_row[4];
+      uint32_t slab_row[8];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
+      for (int s = 0; s < 8; ++s) {
         const int ohl = (16 * s) / p.Wo, ow0 = (16 * s) - ohl * p.Wo;
         slab_row[s] = static_cast<uint32_t>(ohl * p.Ws + ow0);
       }
@@ -112,10 +115,9 @@ cl_resident_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __gri
         for (int t = 0; t < p.n_tiles; ++t) {
           const uint32_t idesc = umma_idesc_f16(128, static_cast<uint32_t>(64 * p.tile_ndw[t]), 1u);
           const uint32_t woff = static_cast<uint32_t>(p.tile_woff[t]);
-          const uint64_t b0 = bdesc_y0 + static_cast<uint64_t>((slab_row[0] + woff) * 8u);
-          const uint64_t b1 = bdesc_y0 + static_cast<uint64_t>((slab_row[1] + woff) * 8u);
-          const uint64_t b2 = bdesc_y0 + static_cast<uint64_t>((slab_row[2] + woff) * 8u);
-          const uint64_t b3 = bdesc_y0 + static_cast<uint64_t>((slab_row[3] + woff) * 8u);
+          uint64_t bs[8];
+#pragma unroll
+          for (int s = 0; s < 8; ++s) bs[s] = bdesc_y0 + static_cast<uint64_t>((slab_row[s] + woff) * 8u);
           mbar_wait(&acc_empty[acc], aph ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -124,12 +126,14 @@ cl_resident_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __gri
             mbar_wait(&y_full[st], yph);
             tc_fence_after();
             const uint64_t yo = static_cast<uint64_t>(st * (kResYStride >> 4));
-            umma_f16(tmem_d, adesc, b0 + yo, idesc, kb > 0 ? 1u : 0u);
-            umma_f16(tmem_d, adesc + 128, b1 + yo, idesc, 1u);
-            umma_f16(tmem_d, adesc + 256, b2 + yo, idesc, 1u);
-            umma_f16(tmem_d, adesc + 384, b3 + yo, idesc, 1u);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              // slab s: X box s/4 (16 KB apart), rows 16*(s%4) of it
+              umma_f16(tmem_d, adesc + static_cast<uint64_t>((s >> 2) * 1024 + (s & 3) * 128), bs[s] + yo, idesc,
+                       (kb > 0 || s > 0) ? 1u : 0u);
+            }
             umma_commit(&y_empty[st]);
-            adesc += 1024;                           // next k-block of X: 16 KB
+            adesc += 2048;                           // next k-block of X: two 16 KB boxes
             if (++st == kResYStages) { st = 0; yph ^= 1; }
           }
           umma_commit(&acc_full[acc]);

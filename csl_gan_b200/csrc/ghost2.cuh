@@ -294,22 +294,33 @@ ghost2_norm_kernel(const __grid_constant__ CUtensorMap tmap_xt, const __grid_con
         else if (len == 2) run_planes(std::integral_constant<int, 2>{});
         else if (len == 1) run_planes(std::integral_constant<int, 1>{});
         else {
-          // long ranges (few (sample, q) pairs per thread budget): 4 values of q' at a time
+          // long ranges (few (sample, q) pairs per thread budget; the 8x8 layer: 64 values of q' per thread): blocks of
+          // 16 values of q' with their row addresses and running sums in registers, explicit shared-memory loads (the
+          // first version walked generic pointers 4 at a time: LD.E with 64-bit address arithmetic, ncu source page).
+          // The product with BB is folded in per plane, so nothing but `acc` lives across planes.
           for (int pl = 0; pl < p.n_planes; ++pl) {
             copy_plane();
             if (worker) {
               const int t0 = p.plane_tap0[pl], t1 = p.plane_tap0[pl + 1];
-              for (int i = 0; i + 4 <= len; i += 4) {
-                const float* p0 = pbase + arow[i];
-                const float* p1 = pbase + arow[i + 1];
-                const float* p2 = pbase + arow[i + 2];
-                const float* p3 = pbase + arow[i + 3];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              int i = 0;
+              for (; i + 16 <= len; i += 16) {
+                uint32_t ptr[16];
+                float sum[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { ptr[j] = smem_u32(pbase + arow[i + j]); sum[j] = 0.f; }
                 for (int t = t0; t < t1; ++t) {
-                  const int sh = p.tap_shift[t] * kShiftMul;
-                  s0 += p0[sh]; s1 += p1[sh]; s2 += p2[sh]; s3 += p3[sh];
+                  const uint32_t sh = static_cast<uint32_t>(p.tap_shift[t] * kShiftMul * 4);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) sum[j] += lds_f32(ptr[j] + sh);
                 }
-                acc = fmaf(brow[i], s0, fmaf(brow[i + 1], s1, fmaf(brow[i + 2], s2, fmaf(brow[i + 3], s3, acc))));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc = fmaf(brow[i + j], sum[j], acc);
+              }
+              for (; i < len; ++i) {
+                const uint32_t p0 = smem_u32(pbase + arow[i]);
+                float s0 = 0.f;
+                for (int t = t0; t < t1; ++t) s0 += lds_f32(p0 + static_cast<uint32_t>(p.tap_shift[t] * kShiftMul * 4));
+                acc = fmaf(brow[i], s0, acc);
               }
             }
             epi_bar_sync();
