@@ -1099,15 +1099,13 @@ static int res_mode() {
   return m;
 }
 
-int launch_resident_norm(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, int sm_count,
-                         cg_stream_t stream) {
-  const int mode = res_mode();
-  if (!(mode & 4)) return 1;
+// geometry + tile table shared by the two resident kernels; 0 = covered, 1 = not covered
+static int res_fill(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg::ResParams* pp) {
+  cg::ResParams& p = *pp;
   const int Q = g->Ho * g->Wo;
   if (!d->half || plan->merged || plan->cw != 64 || plan->Cp != 64 || d->M > 128 || (g->Wo != 16 && g->Wo != 32 && g->Wo != 64) ||
       Q % cg::kResKb || static_cast<long long>(Q) * 256 > cg::kResXBytes || (d->n_seg > 1))
     return 1;
-  cg::ResParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->M; p.Q = Q; p.Wo = g->Wo; p.Ws = plan->Ws; p.nkb = Q / cg::kResKb; p.kb_h = cg::kResKb / g->Wo; p.n_cb = 1;
   p.y_bytes = 128 * plan->Ws * p.kb_h;
@@ -1117,45 +1115,87 @@ int launch_resident_norm(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_
   bool used[CG_MAX_KH * CG_MAX_KH] = {false};
   for (int t = 0; t < n_taps; ++t) {
     if (used[t]) continue;
-    int lo = plan->tap_woff[t], hi = lo;
+    int lo = plan->tap_woff[t], hi = lo, cnt = 0;
     for (int u = 0; u < n_taps; ++u)
       if (plan->tap_plane[u] == plan->tap_plane[t] && plan->tap_hoff[u] == plan->tap_hoff[t]) {
-        used[u] = true;
+        used[u] = true; ++cnt;
         if (plan->tap_woff[u] < lo) lo = plan->tap_woff[u];
         if (plan->tap_woff[u] > hi) hi = plan->tap_woff[u];
       }
-    int cnt = 0;
-    for (int u = 0; u < n_taps; ++u)
-      if (plan->tap_plane[u] == plan->tap_plane[t] && plan->tap_hoff[u] == plan->tap_hoff[t]) ++cnt;
     if (cnt != hi - lo + 1 || cnt > 4 || p.n_tiles >= cg::kResMaxTiles) return 1;     // shifts must be consecutive
-    p.tile_plane[p.n_tiles] = plan->tap_plane[t]; p.tile_hoff[p.n_tiles] = plan->tap_hoff[t];
-    p.tile_woff[p.n_tiles] = lo; p.tile_ndw[p.n_tiles] = cnt;
-    ++p.n_tiles;
+    const int k = p.n_tiles++;
+    p.tile_plane[k] = plan->tap_plane[t]; p.tile_hoff[k] = plan->tap_hoff[t];
+    p.tile_woff[k] = lo; p.tile_ndw[k] = cnt;
+    for (int u = 0; u < n_taps; ++u)
+      if (plan->tap_plane[u] == plan->tap_plane[t] && plan->tap_hoff[u] == plan->tap_hoff[t])
+        p.tile_tap[k][plan->tap_woff[u] - lo] = u;
   }
   // the last slab of a k-block must end inside the plane box
   for (int t = 0; t < p.n_tiles; ++t) {
     const int last = (p.kb_h - 1) * plan->Ws + (g->Wo - 16) + p.tile_woff[t] + p.tile_ndw[t] - 1 + 15;
     if (last >= plan->Ws * p.kb_h) return 1;
   }
-  p.slot_lo = d->slot_lo; p.n_groups = d->n_groups; p.out = d->out; p.inv_x = d->inv_x; p.inv_y = d->inv_y;
-  p.flags = mode & 3;
+  p.slot_lo = d->slot_lo; p.inv_x = d->inv_x; p.inv_y = d->inv_y;
+  return 0;
+}
+
+typedef void (*ResKernel)(const CUtensorMap, const CUtensorMap, const cg::ResParams);
+static int res_launch(ResKernel kernel, const cg_cl_desc* d, const cg_cl_plan* plan, const cg::ResParams& p, int smem, long long grid,
+                      bool* attr_set, cg_stream_t stream) {
   CUtensorMap tx, ty;
   if (make_cl_tmaps(&tx, &ty, d, plan, 1, 64, plan->Ws, p.kb_h, 1, 1)) return -1;
+  if (!*attr_set) {
+    if (cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess) {
+      fail("resident kernel: shared memory attribute"); return -1;
+    }
+    *attr_set = true;
+  }
+  kernel<<<static_cast<int>(grid), cg::kClThreads, smem, S(stream)>>>(tx, ty, p);
+  if (cudaGetLastError() != cudaSuccess) { fail("resident kernel launch failed"); return -1; }
+  return 0;
+}
+
+int launch_resident_norm(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, int sm_count,
+                         cg_stream_t stream) {
+  if (!(res_mode() & 4)) return 1;
+  cg::ResParams p;
+  if (res_fill(d, g, plan, &p)) return 1;
+  p.n_groups = d->n_groups; p.out = d->out;
   const int smem = 1024 + 2 * cg::kResXBytes + cg::kResYStages * cg::kResYStride + 512;
   static bool attr_set[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { fail("cudaGetDevice failed"); return -1; }
-  if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(cg::cl_resident_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      fail("cl_resident_norm_kernel: shared memory attribute"); return -1;
-    }
-    attr_set[dev] = true;
-  }
   long long grid = d->max_ctas > 0 ? d->max_ctas : sm_count;
   if (grid > p.n_groups) grid = p.n_groups;
-  cg::cl_resident_norm_kernel<<<static_cast<int>(grid), cg::kClThreads, smem, S(stream)>>>(tx, ty, p);
-  if (cudaGetLastError() != cudaSuccess) { fail("cl_resident_norm_kernel launch failed"); return -1; }
-  return 0;
+  return res_launch(cg::cl_resident_norm_kernel, d, plan, p, smem, grid, &attr_set[dev], stream);
+}
+
+// split-K clipped sum with resident backprops (cl_res.cuh); out must be the gradient-natural layout
+int launch_resident_sum(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, int sm_count,
+                        cg_stream_t stream) {
+  if (!(res_mode() & 4) || (res_mode() & 8)) return 1;             // CSLGAN_RESIDENT=12: norms only
+  cg::ResParams p;
+  if (res_fill(d, g, plan, &p)) return 1;
+  if (plan->Cs > 64 || d->slot_hi <= d->slot_lo) return 1;
+  p.slot_hi = d->slot_hi;
+  p.n_tp = (p.n_tiles + 1) / 2;
+  long long ctas = d->max_ctas > 0 ? d->max_ctas : sm_count;
+  const int n_samples = d->slot_hi - d->slot_lo;
+  int G = static_cast<int>(ctas / p.n_tp);
+  if (G < 1) G = 1;
+  if (G > n_samples) G = n_samples;
+  p.spg = (n_samples + G - 1) / G;
+  p.n_groups = (n_samples + p.spg - 1) / p.spg;
+  p.C = plan->Cs; p.ldT = static_cast<long long>(plan->n_taps) * plan->Cs;
+  p.out = d->out; p.out_scale = d->out_scale;
+  const int smem = 1024 + 2 * cg::kResXBytes + cg::kResYStages * cg::kResYStride + 4 * cg::kResSumEpiFloats * 4 + 512;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { fail("cudaGetDevice failed"); return -1; }
+  long long grid = ctas;
+  if (grid > static_cast<long long>(p.n_tp) * p.n_groups) grid = static_cast<long long>(p.n_tp) * p.n_groups;
+  return res_launch(cg::cl_resident_sum_kernel, d, plan, p, smem, grid, &attr_set[dev], stream);
 }
 
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream) {
@@ -1167,6 +1207,11 @@ int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_pla
   const int Q = g->Ho * g->Wo;
   if (d->half && d->group_mode == CG_GROUP_SAMPLE && d->epi == CG_EPI_SUMSQ && !d->pair && d->inv_x && d->inv_y) {
     const int rc = launch_resident_norm(d, g, plan, dv.sm, stream);
+    if (rc == 0) return 0;
+    if (rc < 0) return 1;
+  }
+  if (d->half && d->group_mode == CG_GROUP_SPLITK && d->epi == CG_EPI_ACCUM && !d->pair) {
+    const int rc = launch_resident_sum(d, g, plan, dv.sm, stream);
     if (rc == 0) return 0;
     if (rc < 0) return 1;
   }
