@@ -379,7 +379,7 @@ def other_configs(dev, args, peaks, only=None):
                                    conditional_arch=o.conditional_arch, aux_loss_type=o.aux_loss_type,
                                    aux_loss_scalar=o.aux_loss_scalar, weights_seed=o.weights_seed, device=dev)
         shape = (1, 28, 28) if o.dataset == "MNIST" else (3, o.im_size, o.im_size)
-        if o.dataset == "CelebA":
+        if o.dataset == "CelebA" and not (o.dp_mode == "is" and os.environ.get("CSLGAN_IS_CL", "1") == "0"):
             D = D.to(memory_format=torch.channels_last)
         opt_d = torch.optim.Adam(D.parameters(), lr=o.d_lr, betas=(o.adam_b1, o.adam_b2), capturable=True)
         eng = setup_privacy_engine(o, D, opt_d)

@@ -18,7 +18,7 @@ for r in data:
     bw = num(r, "dram__bytes.sum.per_second") * scale[units[c("dram__bytes.sum.per_second")]]
     by = bw * t
     st = sorted(((num(r, s), s[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for s in stalls), reverse=True)[:3]
-    grp = "contract" if any(x in k for x in ("contract", "pair", "ghost")) else ("stage" if ("stage" in k or "absmax" in k) else "other")
+    grp = "contract" if any(x in k for x in ("contract", "pair", "ghost", "resident")) else ("stage" if ("stage" in k or "absmax" in k) else "other")
     a = tot.setdefault(grp, [0.0, 0.0]); a[0] += t; a[1] += by
     print(f"{k:34s} {t*1e6:7.1f} {by/1e6:8.1f} {num(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} "
           f"{num(r,'lts__throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} {num(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f} "
