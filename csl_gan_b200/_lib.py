@@ -253,7 +253,7 @@ def noise_multi_allreduce(segs, mean: bool, seed, offset, offset_dev, local_flat
     `mc_ptr` of the symmetric buffer `local_flat` (or, mc_ptr = 0, over the peer mappings `peer_ptrs`); `segs` as in
     noise_multi.  Returns the generator-offset advance."""
     peers = None
-    if not mc_ptr:
+    if peer_ptrs:
         peers = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
     arr = (NoiseSeg * len(segs))()
     for i, (tin, tg, mult, sdev) in enumerate(segs):

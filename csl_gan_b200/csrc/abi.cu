@@ -1491,7 +1491,7 @@ int noise_multi_impl(const cg_noise_seg* segs, int n_segs, double in_div, const 
                      double noise_div, const float* noise_div_dev, unsigned long long seed,
                      unsigned long long offset, const unsigned long long* offset_dev,
                      unsigned long long* offset_inc, const float* local_base, float* mc_base, float* const* peers,
-                     long long buf_len, long long count_off, int rank, int world, cg_stream_t stream) {
+                     long long buf_len, long long count_off, int rank, int world, cg_stream_t stream, int mc_mode = 3) {
   const bool ar = mc_base != nullptr || peers != nullptr;
   if (offset_inc) *offset_inc = 0;
   if (n_segs <= 0) return 0;
@@ -1538,6 +1538,7 @@ int noise_multi_impl(const cg_noise_seg* segs, int n_segs, double in_div, const 
     p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
     p.local_base = local_base; p.mc_base = mc_base; p.count_off = count_off; p.rank = rank; p.world = world;
     if (peers) for (int r = 0; r < world && r < 8; ++r) p.peer[r] = peers[r];
+    p.ld_mc = (mc_base && (mc_mode & 1)) ? 1 : 0; p.st_mc = (mc_base && (mc_mode & 2)) ? 1 : 0;
     long long grid = ar ? (blk + world - 1) / world : blk;
     const long long cap = static_cast<long long>(d.sm) * 8;
     if (grid > cap) grid = cap;
@@ -1567,13 +1568,19 @@ int cg_noise_finalize_allreduce(const cg_noise_seg* segs, int n_segs, int mean, 
   if (!local_base || (!mc_base && !peers)) return fail("null symmetric base / neither a multicast nor peer mappings");
   if (world < 1 || rank < 0 || rank >= world) return fail("bad rank %d of %d", rank, world);
   if (!mc_base && world > 8) return fail("the peer-to-peer exchange covers up to 8 ranks");
-  if (!mc_base && peers[rank] != local_base) return fail("peers[rank] must be this rank's own buffer");
+  if (peers && peers[rank] != local_base) return fail("peers[rank] must be this rank's own buffer");
+  // both mappings given: loads through the switch (one reduced reply per request instead of `world` round trips),
+  // stores through the peer mappings -- or the other way round (CSLGAN_XFER_MIX=1: multicast loads, 2: multicast stores)
+  const char* mix_env = getenv("CSLGAN_XFER_MIX");                     // (read per call: a probe switches it at run time)
+  const int mix = mix_env ? atoi(mix_env) : 0;
+  const int mc_mode = (mc_base && peers && (mix == 1 || mix == 2)) ? mix : 3;
+  if (mc_base && peers && world > 8) return fail("the peer-to-peer exchange covers up to 8 ranks");
   if (count_off >= buf_len) return fail("count element outside the buffer");
   if (mean && count_off < 0) return fail("mean reduction needs the sample-count element");
   // mean: both divisors are the all-rank sample count the kernel reads through the switch (1.0 only marks them active)
   return noise_multi_impl(segs, n_segs, mean ? 1.0 : 0.0, nullptr, mean ? 1.0 : 0.0, nullptr, seed, offset, offset_dev,
-                          offset_inc, local_base, mc_base, mc_base ? nullptr : peers, buf_len, mean ? count_off : -1, rank,
-                          world, stream);
+                          offset_inc, local_base, mc_base, (mc_base && mc_mode == 3) ? nullptr : peers, buf_len,
+                          mean ? count_off : -1, rank, world, stream, mc_mode);
 }
 
 int cg_noise_finalize(const float* in, float* grad, long long n, double in_div, double std, double noise_div,

@@ -563,6 +563,7 @@ struct NoiseParams {
   // peer-to-peer variant (mc_base == nullptr): the same buffer on every rank through its NVLink peer mapping; the sum
   // is formed in rank order from plain 16-byte loads and the result stored to every peer
   float* peer[8];
+  int ld_mc, st_mc;                    // loads / stores through the multicast mapping (when mc_base is set); else peers
 };
 
 
@@ -590,7 +591,7 @@ __device__ __forceinline__ void multimem_st4(float* mc, float4 v) {
 }
 
 __device__ __forceinline__ float4 ar_load4(const NoiseParams& p, long long off) {
-  if (p.mc_base) return multimem_ld_sum4(p.mc_base + off);
+  if (p.ld_mc) return multimem_ld_sum4(p.mc_base + off);
   // all loads first (eight independent 16-byte requests in flight per thread), then the sum in rank order
   float4 b[8];
 #pragma unroll
@@ -604,19 +605,19 @@ __device__ __forceinline__ float4 ar_load4(const NoiseParams& p, long long off) 
   return a;
 }
 __device__ __forceinline__ float ar_load1(const NoiseParams& p, long long off) {
-  if (p.mc_base) return multimem_ld_sum(p.mc_base + off);
+  if (p.ld_mc) return multimem_ld_sum(p.mc_base + off);
   float a = p.peer[0][off];
   for (int r = 1; r < p.world; ++r) a += p.peer[r][off];
   return a;
 }
 __device__ __forceinline__ void ar_store4(const NoiseParams& p, long long off, float4 v) {
-  if (p.mc_base) { multimem_st4(p.mc_base + off, v); return; }
+  if (p.st_mc) { multimem_st4(p.mc_base + off, v); return; }
 #pragma unroll
   for (int r = 0; r < 8; ++r)
     if (r < p.world) __stcg(reinterpret_cast<float4*>(p.peer[r] + off), v);
 }
 __device__ __forceinline__ void ar_store1(const NoiseParams& p, long long off, float v) {
-  if (p.mc_base) { multimem_st(p.mc_base + off, v); return; }
+  if (p.st_mc) { multimem_st(p.mc_base + off, v); return; }
   for (int r = 0; r < p.world; ++r) p.peer[r][off] = v;
 }
 

@@ -109,7 +109,8 @@ class SymmetricFlat:
         # 84 us NCCL+noise; 8 GPUs 66 / 147 / ~150 us.  CSLGAN_XFER=p2p|multimem overrides.
         import os
         want = os.environ.get("CSLGAN_XFER", "")
-        self.use_multicast = all(self.mc_ptrs) and (want == "multimem" or (want != "p2p" and self.world > 8))
+        self.use_multicast = all(self.mc_ptrs) and (want in ("multimem", "mix") or (want != "p2p" and self.world > 8))
+        self.mix = want == "mix"                             # both mappings to the kernel (CSLGAN_XFER_MIX picks the halves)
         if not self.use_multicast and self.world > 8:
             raise RuntimeError("peer-to-peer exchange covers up to 8 ranks and there is no multicast mapping")
 

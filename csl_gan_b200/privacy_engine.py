@@ -1007,7 +1007,8 @@ class PrivacyEngine:
             flat[self._n_theta:].fill_(bs)
             sy.barrier(fused_i)                              # every rank's sums (and count) are written
             inc = L.noise_multi_allreduce(segs, mean, self._seed, 0 if od is not None else self._philox_offset, od,
-                                          flat, sy.mc_ptrs[fused_i] if sy.use_multicast else 0, sy.peer_ptrs[fused_i],
+                                          flat, sy.mc_ptrs[fused_i] if sy.use_multicast else 0,
+                                          sy.peer_ptrs[fused_i] if (sy.mix or not sy.use_multicast) else None,
                                           self._n_theta, sy.rank, sy.world, st)
             sy.barrier(fused_i)                              # every rank's share of the result has landed everywhere
         else:
