@@ -629,3 +629,41 @@ def test_engine_rejects_cpu_module_and_batchnorm():
     bad = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4)).to(DEV)
     with pytest.raises(NotImplementedError):
         cg.PrivacyEngine(bad, batch_size=4, sample_size=100, noise_multiplier=1.0, max_grad_norm=1.0)
+
+
+def test_device_mean_sampler_matches_reference_expressions():
+    """DeviceMeanSampler on the GPU against the reference's expressions (mean_sampler.py:47-64 class means,
+    :75-84 sample): exact with the noise switched off, and the two noise terms have the reference's structure (one
+    offset per sample + iid pixel noise) and scale with it on."""
+    from csl_gan_b200.mean_sampler import DeviceMeanSampler
+    g = torch.Generator().manual_seed(3)
+    n_classes, mean_size, n_batches = 3, 20, 4
+    batches = [(torch.rand(90, 1, 8, 8, generator=g), torch.randint(0, n_classes, (90,), generator=g)) for _ in range(n_batches)]
+    ms = DeviceMeanSampler.from_batches(batches, n_classes, mean_size, 0.0, 60000, device=DEV)
+    assert ms.mean_samples.is_cuda and tuple(ms.mean_samples.shape) == (n_classes, n_batches, 1, 8, 8)
+    for i, (x, y) in enumerate(batches):
+        for c in range(n_classes):
+            s = x[y == c]
+            want = (s[:mean_size] if len(s) > mean_size else s).sum(dim=0) / mean_size       # reference :57-59
+            assert torch.allclose(ms.mean_samples[c, i].cpu(), want, atol=1e-6)
+    # sample(): every block of num_samples draws is a permutation of the stored means (reference :76), labels honoured
+    labels = torch.randint(0, n_classes, (10,), generator=g)
+    r, lab = ms.sample(10, noise_std=0.0, noise_mean_std=0.0, requested_labels=labels)
+    assert r.is_cuda and torch.equal(lab.cpu(), labels)
+    stored = ms.mean_samples.cpu()
+    for blk in range(0, 10, n_batches):
+        idx = []
+        for k in range(blk, min(blk + n_batches, 10)):
+            hit = [j for j in range(n_batches) if torch.equal(r[k].cpu(), stored[labels[k], j])]
+            assert len(hit) >= 1
+            idx.append(hit[0])
+        assert len(set(idx)) == len(idx)                                                     # no repeats inside a block
+    # noise structure: r - mean = per-sample constant (std noise_mean_std) + iid pixel noise (std noise_std)
+    big = DeviceMeanSampler(torch.zeros(1, 4, 1, 32, 32, device=DEV), 0.1, 100, 60000)
+    r, lab = big.sample(512, noise_std=0.05, noise_mean_std=0.2)
+    assert lab is None and tuple(r.shape) == (512, 1, 32, 32)
+    per_sample = r.mean(dim=(1, 2, 3))
+    assert abs(per_sample.std().item() - 0.2) < 0.03
+    assert abs((r - per_sample.view(-1, 1, 1, 1)).std().item() - 0.05) < 0.005
+    eps, alpha = big.get_privacy_cost(1e-6)
+    assert eps > 0 and alpha > 1
