@@ -578,8 +578,9 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
     contract_calls = ("cg_cl_contract", "cg_ghost_norm", "cg_contract")
     out["t_contract"] = sum(per_step.get(k, (0.0, 0))[0] for k in contract_calls)
     out["n_contract"] = sum(per_step.get(k, (0.0, 0))[1] for k in contract_calls)
-    out["t_thin"] = per_step.get("cg_thin_capture", (0.0, 0))[0]
-    out["n_thin"] = per_step.get("cg_thin_capture", (0.0, 0))[1]
+    thin_calls = ("cg_thin_capture", "cg_thin_capture2")
+    out["t_thin"] = sum(per_step.get(k, (0.0, 0))[0] for k in thin_calls)
+    out["n_thin"] = sum(per_step.get(k, (0.0, 0))[1] for k in thin_calls)
     out["flops_step"] = 2 * B * cfg["fpsg"]
     out["kernel_ms_per_step"] = {k: round(v[0], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][0])}
     if not do_e2e:

@@ -84,6 +84,11 @@ class SmallOp(C.Structure):
                 ("c", C.c_void_p), ("out", C.c_void_p), ("out2", C.c_void_p)]
 
 
+class ScaleSeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("mult", C.c_void_p), ("pitch", C.c_longlong),
+                ("slot_stride", C.c_longlong), ("rows", C.c_int), ("slot_lo", C.c_int), ("slot_hi", C.c_int)]
+
+
 class NoiseSeg(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("grad", C.c_void_p), ("n", C.c_longlong), ("std_mult", C.c_double),
                 ("std_dev", C.c_void_p)]
@@ -117,11 +122,15 @@ _PROTOS = {
     "cg_stage_yt_h": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                 C.POINTER(UnfoldGeom), C.POINTER(GhostPlan), C.c_float, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_scale_slots_h_multi": (C.c_int, [C.POINTER(ScaleSeg), C.c_int, C.c_void_p]),
     "cg_small_ops": (C.c_int, [C.POINTER(SmallOp), C.c_int, C.c_void_p]),
     "cg_thin_direct_ok": (C.c_int, [C.POINTER(UnfoldGeom), C.c_int]),
     "cg_thin_capture": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p,
                                   C.c_int, C.POINTER(UnfoldGeom), C.c_int, C.c_float, C.c_void_p, C.c_longlong,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cg_thin_capture2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.POINTER(UnfoldGeom), C.c_int, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_clip_mult": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cg_scale_slots_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p]),
@@ -283,6 +292,17 @@ def small_ops(ops, stream):
             arr[j].op, arr[j].R, arr[j].lo, arr[j].n = op, int(R), int(lo), int(n)
             arr[j].a, arr[j].b, arr[j].c, arr[j].out, arr[j].out2 = ptr(a), ptr(b), ptr(c), ptr(out), ptr(out2)
         call("cg_small_ops", arr, len(chunk), stream)
+
+
+def scale_slots_multi(segs, stream):
+    """One launch of cg_scale_slots_h_multi over segs = [(src, dst, mult, pitch, slot_stride, rows, slot_lo, slot_hi)]."""
+    for i in range(0, len(segs), 8):
+        chunk = segs[i:i + 8]
+        arr = (ScaleSeg * len(chunk))()
+        for j, (src, dst, mult, pitch, stride, rows, lo, hi) in enumerate(chunk):
+            arr[j].src, arr[j].dst, arr[j].mult = ptr(src), ptr(dst), ptr(mult)
+            arr[j].pitch, arr[j].slot_stride, arr[j].rows, arr[j].slot_lo, arr[j].slot_hi = int(pitch), int(stride), int(rows), int(lo), int(hi)
+        call("cg_scale_slots_h_multi", arr, len(chunk), stream)
 
 
 def cl_pair_ok(M: int, geom, plan) -> bool:

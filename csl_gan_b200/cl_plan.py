@@ -111,6 +111,7 @@ class ClLayerPlan:
             self.Xt = self.Xc = self.Yt = None
             self.gnorm2 = torch.zeros(S, device=dev)
             self._act = {}
+            self._pending = []                     # (act, grad_output, slot0, scale) captures not launched yet
         else:
             self.Xt = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
             self.Xc = torch.zeros((self.x_chunks, self.x_rows, cw), device=dev, dtype=dt)
@@ -181,12 +182,33 @@ class ClLayerPlan:
     def capture_activation(self, act: torch.Tensor, pass_idx: int):
         slot0 = pass_idx * self.Bpad
         if self.direct:
+            if pass_idx == 0:
+                self._pending = []                     # a new step: nothing of an abandoned one may linger
             self._act[pass_idx] = act                  # read by cg_thin_capture when the backprops arrive
             return
         if self.kind == "convT":
             self._stage_x(act, slot0, 1.0, None, None)
         else:
             self._stage_y(act, slot0, 1.0)
+
+    def flush_direct(self):
+        """Launch the deferred thin-layer captures (cg_thin_capture2 for a pair with equal strides and scale)."""
+        pend, self._pending = self._pending, []
+        while pend:
+            act, g, slot0, scale = pend.pop(0)
+            sn, sc, sh, sw = _strides4(act)
+            st = L.stream_ptr(g.device)
+            bias = self.bias_rows
+            if pend and _strides4(pend[0][0]) == (sn, sc, sh, sw) and pend[0][3] == scale:
+                act2, g2, slot2, _ = pend.pop(0)
+                L.call("cg_thin_capture2", L.ptr(act), L.ptr(act2), sn, sc, sh, sw, L.ptr(g), L.ptr(g2), g.shape[0], g2.shape[0],
+                       C.byref(self.geom), self.M, scale, L.ptr(self.Gs[slot0:]), L.ptr(self.Gs[slot2:]), self.Gs.shape[1],
+                       L.ptr(self.gnorm2[slot0:]), L.ptr(self.gnorm2[slot2:]),
+                       L.ptr(bias[slot0:]) if bias is not None else None, L.ptr(bias[slot2:]) if bias is not None else None, st)
+            else:
+                L.call("cg_thin_capture", L.ptr(act), sn, sc, sh, sw, L.ptr(g), g.shape[0], C.byref(self.geom), self.M, scale,
+                       L.ptr(self.Gs[slot0:]), self.Gs.shape[1], L.ptr(self.gnorm2[slot0:]),
+                       L.ptr(bias[slot0:]) if bias is not None else None, st)
 
     def capture_backprop(self, g: torch.Tensor, pass_idx: int, scale: float):
         slot0 = pass_idx * self.Bpad
@@ -195,10 +217,11 @@ class ClLayerPlan:
             if act is None or act.shape[0] != g.shape[0]:
                 raise L.CslGanCudaError(f"{self.name}: backprops of pass {pass_idx} arrived without their activation")
             g = g.contiguous(memory_format=torch.channels_last)       # dense [B][Ho*Wo][M]; a no-op for a channels_last critic
-            sn, sc, sh, sw = _strides4(act)
-            L.call("cg_thin_capture", L.ptr(act), sn, sc, sh, sw, L.ptr(g), g.shape[0], C.byref(self.geom), self.M, scale,
-                   L.ptr(self.Gs[slot0:]), self.Gs.shape[1], L.ptr(self.gnorm2[slot0:]),
-                   L.ptr(self.bias_rows[slot0:]) if self.bias_rows is not None else None, L.stream_ptr(g.device))
+            # the launch is deferred until the other passes of the step have arrived (or the norms are asked for): both
+            # passes in ONE launch waste less of the last round of the 148 persistent CTAs than two launches
+            self._pending.append((act, g, slot0, float(scale)))
+            if len(self._pending) >= min(2, self.max_passes):
+                self.flush_direct()
             return
         if self.kind == "convT":
             self._stage_y(g, slot0, scale)
@@ -265,6 +288,7 @@ class ClLayerPlan:
         d.group_mode, d.n_groups, d.slot_lo, d.slot_hi = L.GROUP_SAMPLE, B, slot0, slot0 + B
         d.n_seg, d.seg_stride = n_joint, self.Bpad
         if self.direct:
+            self.flush_direct()
             self._gs_joint = 1
             if ops is not None:
                 ops.append(L.small_op(L.OP_COPY, self.gnorm2[slot0:], norm2_row[slot0:], B))
@@ -310,6 +334,12 @@ class ClLayerPlan:
             return None
         return L.small_op(L.OP_CLIP_MULT, factor_row, self.mult, slot_hi - slot_lo, b=self.inv_x, c=self.inv_y,
                           out2=self.out_scale, lo=slot_lo)
+
+    def scale_seg(self, slot_lo: int, slot_hi: int):
+        """The cg_scale_slots_h launch of scale_backprops(mult_ready=True) as a cg_scale_slots_h_multi entry, or None."""
+        if self.thin or not self.half:
+            return None
+        return (self.Xt, self.Xc, self.mult, self.x_rows * self.cw, self.Q * self.cw, self.x_chunks, slot_lo, slot_hi)
 
     def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0,
                         mult_ready: bool = False):
@@ -426,6 +456,7 @@ class ClLayerPlan:
         slot0 = pass_idx * self.Bpad
         w = self.layer.weight
         if self.direct:
+            self.flush_direct()
             # Gs[slot][m][kh][kw][c] -> [B][m][c][kh][kw]
             return (self.Gs[slot0:slot0 + B].view(B, self.M, self.KH, self.KW, self.Cn).permute(0, 1, 4, 2, 3)
                     .contiguous())

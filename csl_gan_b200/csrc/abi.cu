@@ -1007,27 +1007,36 @@ int cg_thin_direct_ok(const cg_unfold_geom* g, int M) {
   return thin_smem(p) <= 227 * 1024 ? 1 : 0;
 }
 
-int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long a_sh, long long a_sw, const float* bp,
-                    int B, const cg_unfold_geom* g, int M, float scale, float* Gs, long long gs_stride, float* norm2,
-                    float* bias_rows, cg_stream_t stream) {
+int cg_thin_capture2(const float* act, const float* act2, long long a_sn, long long a_sc, long long a_sh, long long a_sw,
+                     const float* bp, const float* bp2, int B, int B2, const cg_unfold_geom* g, int M, float scale, float* Gs,
+                     float* Gs2, long long gs_stride, float* norm2, float* norm2_2, float* bias_rows, float* bias_rows2,
+                     cg_stream_t stream) {
   if (!act || !bp || !g || !Gs || !norm2) return fail("null argument");
+  if (B2 > 0 && (!act2 || !bp2 || !Gs2 || !norm2_2)) return fail("null argument (second segment)");
+  if (B2 > 0 && ((bias_rows == nullptr) != (bias_rows2 == nullptr))) return fail("bias rows for one segment only");
   if (B <= 0) return 0;
+  if (B2 < 0) B2 = 0;
   cg::ThinParams p;
   if (!cg_thin_direct_ok(g, M) || thin_fill(g, M, &p)) return fail("cg_thin_capture: geometry not covered (cg_thin_direct_ok)");
-  if (static_cast<long long>(B) * p.Q >= (1LL << 31)) return fail("cg_thin_capture: batch too large");
+  if (static_cast<long long>(B > B2 ? B : B2) * p.Q >= (1LL << 31)) return fail("cg_thin_capture: batch too large");
   p.act = act; p.a_sn = a_sn; p.a_sc = a_sc; p.a_sh = a_sh; p.a_sw = a_sw;
-  p.B = B; p.scale = scale;
+  p.B0 = B; p.B = B + B2; p.scale = scale;
   p.Gs = Gs; p.gs_stride = gs_stride; p.norm2 = norm2; p.bias_rows = bias_rows;
+  p.act2 = B2 > 0 ? act2 : act; p.Gs2 = B2 > 0 ? Gs2 : Gs; p.norm2_2 = B2 > 0 ? norm2_2 : norm2;
+  p.bias_rows2 = B2 > 0 ? bias_rows2 : bias_rows;
   DevInfo dv;
   if (dev_info(&dv)) return 1;
   CG_CHECK(cudaMemsetAsync(norm2, 0, sizeof(float) * B, S(stream)));
+  if (B2 > 0) CG_CHECK(cudaMemsetAsync(norm2_2, 0, sizeof(float) * B2, S(stream)));
   // bp: dense channels-last [B*Q rows][M]; box = {32 ch, 64 rows, all chunks} lands as [chunk][row][32 ch]
-  CUtensorMap tb;
-  {
-    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(B) * p.Q, static_cast<cuuint64_t>(p.n_ch)};
+  CUtensorMap tb, tb2;
+  for (int sgi = 0; sgi < 2; ++sgi) {
+    const int nb = sgi == 0 ? B : (B2 > 0 ? B2 : B);
+    const float* base = sgi == 0 ? bp : (B2 > 0 ? bp2 : bp);
+    cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(nb) * p.Q, static_cast<cuuint64_t>(p.n_ch)};
     cuuint64_t str[2] = {static_cast<cuuint64_t>(M) * 4, 128};
     cuuint32_t box[3] = {32, static_cast<cuuint32_t>(cg::kThinKb), static_cast<cuuint32_t>(p.n_ch)};
-    if (make_tmap_nd(&tb, bp, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, false)) return 1;
+    if (make_tmap_nd(sgi == 0 ? &tb : &tb2, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, false)) return 1;
   }
   const int smem = static_cast<int>(thin_smem(p));
   static bool attr_set[64] = {false};
@@ -1037,10 +1046,17 @@ int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long 
     CG_CHECK(cudaFuncSetAttribute(cg::thin_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
-  const int grid = B < dv.sm ? B : dv.sm;
-  cg::thin_direct_kernel<<<grid, cg::kThinThreads, smem, S(stream)>>>(tb, p);
+  const int grid = p.B < dv.sm ? p.B : dv.sm;
+  cg::thin_direct_kernel<<<grid, cg::kThinThreads, smem, S(stream)>>>(tb, tb2, p);
   CG_LAUNCH_CHECK();
   return 0;
+}
+
+int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long a_sh, long long a_sw, const float* bp,
+                    int B, const cg_unfold_geom* g, int M, float scale, float* Gs, long long gs_stride, float* norm2,
+                    float* bias_rows, cg_stream_t stream) {
+  return cg_thin_capture2(act, nullptr, a_sn, a_sc, a_sh, a_sw, bp, nullptr, B, 0, g, M, scale, Gs, nullptr, gs_stride, norm2,
+                          nullptr, bias_rows, nullptr, stream);
 }
 
 int cg_clip_mult(const float* factor, const float* inv_x, const float* inv_y, int slot_lo, int slot_hi, float* mult,
@@ -1081,6 +1097,46 @@ int cg_scale_slots_h(const void* src_half, void* dst_half, int rows, long long p
   cg::scale_slots_half_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const __half*>(src_half),
                                                            static_cast<__half*>(dst_half), rows, pitch,
                                                            static_cast<int>(slot_stride), slot_lo, slot_hi, mult);
+  CG_LAUNCH_CHECK();
+  return 0;
+}
+
+int cg_scale_slots_h_multi(const cg_scale_seg* segs, int n_segs, cg_stream_t stream) {
+  if (n_segs <= 0) return 0;
+  if (!segs) return fail("null segment table");
+  if (n_segs > cg::kScaleMaxSegs) return fail("at most %d segments per cg_scale_slots_h_multi call", cg::kScaleMaxSegs);
+  DevInfo d;
+  if (dev_info(&d)) return 1;
+  cg::ScaleParams p;
+  memset(&p, 0, sizeof(p));
+  long long total_units = 0;
+  for (int i = 0; i < n_segs; ++i)
+    if (segs[i].rows > 0 && segs[i].slot_hi > segs[i].slot_lo)
+      total_units += static_cast<long long>(segs[i].slot_hi - segs[i].slot_lo) * segs[i].slot_stride / 8 * segs[i].rows;
+  if (total_units <= 0) return 0;
+  const long long budget = static_cast<long long>(d.sm) * 8;          // ~8 blocks per SM overall, shared by size
+  int blk = 0, m = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const cg_scale_seg& in = segs[i];
+    if (in.rows <= 0 || in.slot_hi <= in.slot_lo) continue;
+    if (!in.src || !in.dst || !in.mult) return fail("segment %d: null pointer", i);
+    if (in.slot_stride > 0x7fffffffLL || in.slot_stride % 8 || in.pitch % 8 || (reinterpret_cast<uintptr_t>(in.src) & 15) ||
+        (reinterpret_cast<uintptr_t>(in.dst) & 15))
+      return fail("segment %d: cg_scale_slots_h_multi needs 16-byte aligned rows and slot strides", i);
+    cg::ScaleSeg& o = p.seg[m++];
+    o.src = static_cast<const __half*>(in.src); o.dst = static_cast<__half*>(in.dst); o.mult = in.mult;
+    o.pitch = in.pitch; o.rows = in.rows; o.slot_stride = static_cast<int>(in.slot_stride);
+    o.slot_lo = in.slot_lo; o.slot_hi = in.slot_hi;
+    const long long units = static_cast<long long>(in.slot_hi - in.slot_lo) * in.slot_stride / 8 * in.rows;
+    long long nb = (units * budget + total_units - 1) / total_units;
+    const long long cap = (units + 255) / 256;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    o.blk0 = blk; o.nblk = static_cast<int>(nb);
+    blk += o.nblk;
+  }
+  p.n_segs = m;
+  cg::scale_slots_half_multi_kernel<<<blk, 256, 0, S(stream)>>>(p);
   CG_LAUNCH_CHECK();
   return 0;
 }

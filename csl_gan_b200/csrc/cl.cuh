@@ -1105,4 +1105,47 @@ __global__ void scale_slots_half_kernel(const __half* __restrict__ src, __half* 
   }
 }
 
+
+// the same for a table of layers in ONE launch (a step scales 4 operands; the small ones are launch-latency bound)
+constexpr int kScaleMaxSegs = 8;
+struct ScaleSeg {
+  const __half* src;
+  __half* dst;
+  const float* mult;
+  long long pitch;
+  int rows, slot_stride, slot_lo, slot_hi;
+  int blk0, nblk;
+};
+struct ScaleParams {
+  ScaleSeg seg[kScaleMaxSegs];
+  int n_segs;
+};
+
+__global__ void __launch_bounds__(256)
+scale_slots_half_multi_kernel(const __grid_constant__ ScaleParams p) {
+  int k = 0;
+#pragma unroll 1
+  while (k + 1 < p.n_segs && static_cast<int>(blockIdx.x) >= p.seg[k + 1].blk0) ++k;
+  const ScaleSeg& sg = p.seg[k];
+  const long long col0 = static_cast<long long>(sg.slot_lo) * sg.slot_stride;
+  const long long n8 = (static_cast<long long>(sg.slot_hi - sg.slot_lo) * sg.slot_stride) >> 3;
+  const long long total = n8 * sg.rows;
+  const long long step = static_cast<long long>(sg.nblk) * 256;
+  for (long long u = static_cast<long long>(blockIdx.x - sg.blk0) * 256 + threadIdx.x; u < total; u += step) {
+    const long long r = u / n8, i = u - r * n8;
+    const float f = __ldg(sg.mult + sg.slot_lo + static_cast<int>((i << 3) / sg.slot_stride));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(sg.src + r * sg.pitch + col0) + i);
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t ov[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&in[j]));
+      ov[j] = pack_half2(t.x * f, t.y * f);
+    }
+    uint4 o;
+    o.x = ov[0]; o.y = ov[1]; o.z = ov[2]; o.w = ov[3];
+    reinterpret_cast<uint4*>(sg.dst + r * sg.pitch + col0)[i] = o;
+  }
+}
+
 }  // namespace cg

@@ -50,6 +50,13 @@ struct ThinParams {
   float* bias_rows;                                  // [B][M] or null
   int a_bytes, b_bytes, stage_bytes, img_floats;     // A tile (2 atoms of n_g KB), B tile, their sum, one image buffer
   int tmem_cols;
+  // second segment (both passes of a step in ONE launch: 2B items on 148 CTAs waste less of the last round than B
+  // twice): items [B0, B) read act2 / the second tensor map and write Gs2 / norm2_2 / bias_rows2; B0 == B: unused
+  int B0;
+  const float* act2;
+  float* Gs2;
+  float* norm2_2;
+  float* bias_rows2;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
@@ -67,7 +74,8 @@ __device__ __forceinline__ void builder_barrier() {
 }
 
 __global__ void __launch_bounds__(kThinThreads, 1)
-thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_constant__ ThinParams p) {
+thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_constant__ CUtensorMap tmap_bp2,
+                   const __grid_constant__ ThinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* img = reinterpret_cast<float*>(tiles + kThinStages * p.stage_bytes);        // 2 buffers of img_floats
@@ -84,6 +92,7 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
   const int n_ew = (p.Cs + 31) >> 5;                 // epilogue warps that own live accumulator rows
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_bp);
+    tma_prefetch_desc(&tmap_bp2);
     for (int s = 0; s < kThinStages; ++s) {
       mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kThinBuilderWarps); mbar_init(&empty_bar[s], 1);
     }
@@ -104,7 +113,8 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.b_bytes));
-          tma_load_3d(tiles + stage * p.stage_bytes, &tmap_bp, &full_bar[stage], 0, n * p.Q + kb * kThinKb, 0);
+          tma_load_3d(tiles + stage * p.stage_bytes, n < p.B0 ? &tmap_bp : &tmap_bp2, &full_bar[stage], 0,
+                      (n < p.B0 ? n : n - p.B0) * p.Q + kb * kThinKb, 0);
           if (++stage == kThinStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -151,7 +161,8 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * p.M);
-        float* o = p.Gs + static_cast<long long>(n) * p.gs_stride + row;
+        float* o = (n < p.B0 ? p.Gs + static_cast<long long>(n) * p.gs_stride
+                             : p.Gs2 + static_cast<long long>(n - p.B0) * p.gs_stride) + row;
         float ss = 0.f;
         for (int c0 = 0; c0 < p.M; c0 += 16) {
           float v[16];
@@ -170,7 +181,7 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
         if (lane == 0) mbar_arrive(&acc_empty[acc]);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
-        if (lane == 0) atomicAdd(p.norm2 + n, ss);
+        if (lane == 0) atomicAdd(n < p.B0 ? p.norm2 + n : p.norm2_2 + (n - p.B0), ss);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -187,9 +198,10 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
     const uint32_t img_s = smem_u32(img);
     const bool wide = p.a_sw == 1 && (p.Wp & 1) == 0 && (p.P & 1) == 0 && (p.pw & 1) == 0 && (p.Wc & 1) == 0 &&
                       (p.a_sn & 1) == 0 && (p.a_sc & 1) == 0 && (p.a_sh & 1) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.act) & 7) == 0;
+                      (reinterpret_cast<uintptr_t>(p.act) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.act2) & 7) == 0;
     auto issue_image = [&](int n, uint32_t buf_s) {
-      const float* s = p.act + static_cast<long long>(n) * p.a_sn;
+      const float* s = n < p.B0 ? p.act + static_cast<long long>(n) * p.a_sn
+                                : p.act2 + static_cast<long long>(n - p.B0) * p.a_sn;
       for (int line = bw; line < p.C * p.Hc; line += kThinBuilderWarps) {
         const int c = line / p.Hc, h = line - c * p.Hc;
         const float* sr = s + c * p.a_sc + h * p.a_sh;
@@ -295,7 +307,9 @@ thin_direct_kernel(const __grid_constant__ CUtensorMap tmap_bp, const __grid_con
         atomicAdd(&s_bias[bch + 2], b2); atomicAdd(&s_bias[bch + 3], b3);
         builder_barrier();
         if (bt < p.M) {
-          p.bias_rows[static_cast<long long>(n) * p.M + bt] = p.scale * s_bias[bt];
+          float* br = n < p.B0 ? p.bias_rows + static_cast<long long>(n) * p.M
+                               : p.bias_rows2 + static_cast<long long>(n - p.B0) * p.M;
+          br[bt] = p.scale * s_bias[bt];
           s_bias[bt] = 0.f;
         }
       }

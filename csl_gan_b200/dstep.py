@@ -12,6 +12,8 @@ public batch.
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -89,6 +91,10 @@ class DiscriminatorStep:
         # once more): do it once, up front
         self._nhwc = any(p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last)
                          for p in D.parameters())
+        # ... unless the batch is thin (images: 1-4 channels): cuDNN's own conversion of such a batch costs the same as
+        # ours, and the thin-layer kernel (csrc/thin.cuh) copies planar image rows with 8-byte cp.async but has to
+        # gather a channels-last 3-channel image element by element.  CSLGAN_INPUT_NHWC=1 forces the conversion.
+        self._nhwc_min_channels = 1 if os.environ.get("CSLGAN_INPUT_NHWC", "0") == "1" else 16
 
     # ------------------------------------------------------------------ losses (train.py:342-358)
     def _fake_loss(self, fake_img, y):
@@ -156,7 +162,7 @@ class DiscriminatorStep:
         use_gc = opt.dp_mode == "gc" and use_dp
         use_is = opt.dp_mode == "is" and use_dp
         fake_img = fake_img.detach()
-        if self._nhwc and img.dim() == 4:
+        if self._nhwc and img.dim() == 4 and img.shape[1] >= self._nhwc_min_channels:
             img = img.contiguous(memory_format=torch.channels_last)
             fake_img = fake_img.contiguous(memory_format=torch.channels_last)
 

@@ -257,6 +257,12 @@ class LayerPlan:
             return self.impl.clip_mult_op(factor_row, slot_lo, slot_hi)
         return None
 
+    def scale_seg(self, slot_lo: int, slot_hi: int):
+        """cg_scale_slots_h_multi entry equivalent to scale_backprops(mult_ready=True), or None."""
+        if self.impl is not None:
+            return self.impl.scale_seg(slot_lo, slot_hi)
+        return None
+
     def scale_backprops(self, factor_row: torch.Tensor, slot_lo: int, slot_hi: int, factor_shift: int = 0,
                         mult_ready: bool = False):
         """Xc = tf32(X * factor[slot - factor_shift]) over the slot range (clip factors folded into one operand)."""

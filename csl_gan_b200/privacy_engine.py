@@ -810,6 +810,16 @@ class PrivacyEngine:
                                       factor_row=frow_w, prezeroed=True, ops=small)
                     ready.add(("thin", plan))
             L.small_ops(small, st)
+            # ... and the factor-scaled operands of all those layers in ONE launch
+            segs, scaled = [], set()
+            for plan, ranges in todo:
+                if plan in ready and len(ranges) == 1:
+                    sg = plan.scale_seg(ranges[0][0], _round_up(ranges[0][1], 32))
+                    if sg is not None:
+                        segs.append(sg)
+                        scaled.add(plan)
+            if segs:
+                L.scale_slots_multi(segs, st)
         for plan, ranges in todo:
             if ("thin", plan) in ready:
                 continue                                     # its clipped sum was one of the batched operations
@@ -818,7 +828,8 @@ class PrivacyEngine:
             # the contraction reads whole 32-row K blocks, which may reach past `hi` when Q < 32
             if joint or len(ranges) == 1:
                 for lo, hi, shift in ranges:
-                    plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift, mult_ready=plan in ready)
+                    if not (batched and plan in scaled):
+                        plan.scale_backprops(frow_w, lo, _round_up(hi, 32), shift, mult_ready=plan in ready)
                 # the scaled operand now covers every live slot: ONE GEMM over the whole range
                 plan.weighted_sum(outs[plan.w_idx], ranges[0][0], ranges[-1][1], sms, accumulate=False,
                                   factor_row=frow_w, prezeroed=batched)

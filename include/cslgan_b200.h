@@ -274,6 +274,13 @@ int cg_thin_direct_ok(const cg_unfold_geom* g, int M);
 int cg_thin_capture(const float* act, long long a_sn, long long a_sc, long long a_sh, long long a_sw, const float* bp,
                     int B, const cg_unfold_geom* g, int M, float scale, float* Gs, long long gs_stride, float* norm2,
                     float* bias_rows, cg_stream_t stream);
+/* The same for TWO batches in one launch (the fake and the real pass of a D step: 2B items share the 148 persistent
+ * CTAs, which wastes less of the last round than B items twice).  Both image batches have the same strides; the second
+ * segment's outputs are Gs2 / norm2_2 / bias_rows2.  B2 = 0 is cg_thin_capture. */
+int cg_thin_capture2(const float* act, const float* act2, long long a_sn, long long a_sc, long long a_sh, long long a_sw,
+                     const float* bp, const float* bp2, int B, int B2, const cg_unfold_geom* g, int M, float scale, float* Gs,
+                     float* Gs2, long long gs_stride, float* norm2, float* norm2_2, float* bias_rows, float* bias_rows2,
+                     cg_stream_t stream);
 
 /* mult[s] = factor[s] * inv_x[s] * inv_y[s] / 2^E for s in [slot_lo, slot_hi), out_scale[0] = 2^E with 2^E the
  * smallest power of two above max_s factor*inv_x*inv_y (so mult <= 1 and the scaled operand stays in FP16 range;
@@ -284,6 +291,17 @@ int cg_clip_mult(const float* factor, const float* inv_x, const float* inv_y, in
 /* dst[r][slot*stride + q] = fp16(src * mult[slot]) over FP16 rows (the factor-scaled operand of the clipped sum) */
 int cg_scale_slots_h(const void* src_half, void* dst_half, int rows, long long pitch, long long slot_stride,
                      int slot_lo, int slot_hi, const float* mult, cg_stream_t stream);
+/* cg_scale_slots_h for up to 8 layers in one launch (the factor-scaled operands of all layers of a step) */
+typedef struct {
+  const void* src;
+  void* dst;
+  const float* mult;
+  long long pitch;
+  long long slot_stride;
+  int rows;
+  int slot_lo, slot_hi;
+} cg_scale_seg;
+int cg_scale_slots_h_multi(const cg_scale_seg* segs, int n_segs, cg_stream_t stream);
 /* cg_outer_rows_cl over FP16 operands: out = Xt*Yt * inv_x[slot]*inv_y[slot] */
 int cg_outer_rows_cl_h(const void* Xt_half, long long x_rows, const void* Yt_half, long long y_rows, int M, int P,
                        int slot0, int B, const float* inv_x, const float* inv_y, float* out, cg_stream_t stream);
@@ -318,6 +336,12 @@ int cg_cl_kblock_rows(const cg_unfold_geom* g, int half, int* kb_rows, int* kb_s
 /* 1 when cg_cl_contract accepts d->pair = 1 for this layer (split-K clipped sum), else 0 */
 int cg_cl_pair_ok(int M, const cg_unfold_geom* g, const cg_cl_plan* plan);
 
+/* Kernel selection inside cg_cl_contract (csrc/abi.cu): FP16 layers whose window grid is 16 / 32 / 64 wide with
+ * C <= 64, M <= 128 and Ho*Wo*256 B <= 64 KB (the 16x16 layer of the CelebA critics) run csrc/cl_res.cuh -- the
+ * sample's backprops resident in shared memory, the filter taps read as shifted windows of ONE shared-memory copy of
+ * the stride-residue plane -- for CG_GROUP_SAMPLE + CG_EPI_SUMSQ and for CG_GROUP_SPLITK + CG_EPI_ACCUM; d->pair = 1
+ * selects the CTA-pair kernel (csrc/cl_pair.cuh); everything else the tap-per-box kernel (csrc/cl.cuh).
+ * CSLGAN_RESIDENT=0 switches the resident kernels off (A/B measurements). */
 int cg_cl_contract(const cg_cl_desc* d, const cg_unfold_geom* g, const cg_cl_plan* plan, cg_stream_t stream);
 
 /* Joint clipping (accum_passes=True: the per-sample gradients of all passes are summed before clipping).

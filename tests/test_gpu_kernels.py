@@ -499,3 +499,67 @@ def test_thin_capture_matches_unfold_einsum(B, Cin, Cout, H, W, k, s, p, d, layo
     assert ((n2.cpu().double() - n2_ref).abs() / n2_ref).max().item() < 2e-3
     b_ref = scale * Bp.double().sum(dim=(2, 3))
     assert ((bias.cpu().double() - b_ref).abs().max() / b_ref.abs().max()).item() < 1e-5
+
+
+def test_small_ops_table_matches_torch():
+    """cg_small_ops: one launch for a table of the per-layer scalar / bias operations, each against plain torch."""
+    g = torch.Generator().manual_seed(9)
+    S = 300
+    rows = torch.randn(S, 77, generator=g).to(DEV)
+    a, b, c = (torch.rand(S, generator=g).to(DEV) + 0.1 for _ in range(3))
+    out_ss = torch.full((S,), -1.0, device=DEV)
+    out_cp = torch.full((S,), -1.0, device=DEV)
+    out_mul = torch.full((S,), -1.0, device=DEV)
+    out_col = torch.zeros(77, device=DEV)
+    big_rows = torch.randn(S, 4800, generator=g).to(DEV)
+    out_big = torch.zeros(4800, device=DEV)
+    mult = torch.full((S,), -1.0, device=DEV)
+    scale = torch.zeros(2, device=DEV)
+    lo, n = 7, 250
+    ops = [L.small_op(L.OP_ROW_SUMSQ, rows, out_ss, S, R=77),
+           L.small_op(L.OP_COPY, a, out_cp, S),
+           L.small_op(L.OP_MUL, a, out_mul, S, b=b),
+           L.small_op(L.OP_WCOLSUM, rows, out_col, n, b=a, R=77, lo=lo),
+           L.small_op(L.OP_WCOLSUM, big_rows, out_big, n, b=b, R=4800, lo=lo),
+           L.small_op(L.OP_CLIP_MULT, a, mult, n, b=b, c=c, out2=scale, lo=lo)]
+    L.small_ops(ops, st())
+    torch.cuda.synchronize()
+    assert torch.allclose(out_ss, (rows * rows).sum(dim=1), rtol=1e-5)
+    assert torch.equal(out_cp, a)
+    assert torch.equal(out_mul, a * b)
+    assert torch.allclose(out_col, (a[lo:lo + n, None] * rows[lo:lo + n]).sum(dim=0), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(out_big, (b[lo:lo + n, None] * big_rows[lo:lo + n]).sum(dim=0), rtol=1e-4, atol=1e-3)
+    prod = (a * b * c)[lo:lo + n]
+    up = scale[0].item()
+    assert up >= prod.max().item() and up / 2 < prod.max().item() * 1.0000001 and np.log2(up) == round(np.log2(up))
+    assert torch.allclose(mult[lo:lo + n] * up, prod, rtol=1e-6)
+    assert (mult[:lo] == -1).all() and (mult[lo + n:] == -1).all()
+
+
+def test_thin_capture_two_batches_in_one_launch():
+    """cg_thin_capture2: the fake and the real pass of a step as two segments of ONE launch (different batch sizes)."""
+    conv, A, Bp, Ho, Wo = _conv_case(7, 3, 64, 64, 64, 5, 2, 2, 1, seed=21)
+    conv2, A2, Bp2, _, _ = _conv_case(4, 3, 64, 64, 64, 5, 2, 2, 1, seed=22)
+    geom = L.UnfoldGeom(3, 64, 64, 5, 5, 2, 2, 2, 2, 1, 1, Ho, Wo)
+    Cs, M, scale = 75, 64, 2.0
+    outs = []
+    a1, a2 = A.to(DEV), A2.to(DEV)
+    b1 = Bp.to(DEV).contiguous(memory_format=torch.channels_last)
+    b2 = Bp2.to(DEV).contiguous(memory_format=torch.channels_last)
+    Gs = torch.full((11, M * Cs), float("nan"), device=DEV)
+    n2 = torch.full((11,), float("nan"), device=DEV)
+    bias = torch.full((11, M), float("nan"), device=DEV)
+    L.call("cg_thin_capture2", a1.data_ptr(), a2.data_ptr(), a1.stride(0), a1.stride(1), a1.stride(2), a1.stride(3),
+           b1.data_ptr(), b2.data_ptr(), 7, 4, C.byref(geom), M, scale, Gs.data_ptr(), Gs[7:].data_ptr(), Gs.shape[1],
+           n2.data_ptr(), n2[7:].data_ptr(), bias.data_ptr(), bias[7:].data_ptr(), st())
+    torch.cuda.synchronize()
+    for (Ai, Bi, lo) in ((A, Bp, 0), (A2, Bp2, 7)):
+        nb = Ai.shape[0]
+        U = F.unfold(Ai.double(), 5, padding=2, stride=2)
+        G = scale * torch.einsum("bmq,bpq->bmp", Bi.double().reshape(nb, M, -1), U)
+        G = G.view(nb, M, 3, 5, 5).permute(0, 1, 3, 4, 2).reshape(nb, -1)
+        got = Gs[lo:lo + nb].cpu().double()
+        assert ((got - G).norm(dim=1) / G.norm(dim=1)).max().item() < 1e-3
+        assert ((n2[lo:lo + nb].cpu().double() - (G * G).sum(dim=1)).abs() / (G * G).sum(dim=1)).max().item() < 2e-3
+        b_ref = scale * Bi.double().sum(dim=(2, 3))
+        assert ((bias[lo:lo + nb].cpu().double() - b_ref).abs().max() / b_ref.abs().max()).item() < 1e-5
