@@ -300,3 +300,39 @@ def test_layer_geometry_matches_torch_output_shapes():
         # "unfolded" operand is the layer OUTPUT's gradient [out_channels, H, W], the plain operand the input
         Cn, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, M = ClLayerPlan.geometry(ct, "convT", x.shape)
         assert (Cn, H, W) == tuple(y.shape[1:]) and (Ho, Wo) == tuple(x.shape[2:]) and M == ct.in_channels
+
+
+def test_thin_direct_geometry_check_is_pure_host_logic(lib):
+    """cg_thin_direct_ok (csrc/thin.cuh coverage) needs no GPU: the CelebA first conv is covered, a window grid that
+    is not a multiple of 64 positions, too many staged rows or an odd number of backprop chunks are not."""
+    def geom(C, H, k, s, p, d=1):
+        Ho = (H + 2 * p - d * (k - 1) - 1) // s + 1
+        return L.UnfoldGeom(C, H, H, k, k, s, s, p, p, d, d, Ho, Ho)
+    assert L.thin_direct_ok(geom(3, 64, 5, 2, 2), 64)           # CelebA D64 blocks.0
+    assert L.thin_direct_ok(geom(1, 32, 3, 1, 1), 32)
+    assert not L.thin_direct_ok(geom(3, 40, 5, 2, 2), 64)       # 20 x 20 = 400 positions: not a multiple of 64
+    assert not L.thin_direct_ok(geom(8, 64, 5, 2, 2), 64)       # 200 staged rows > 128
+    assert not L.thin_direct_ok(geom(3, 64, 5, 2, 2), 96)       # three 32-channel chunks
+    assert not L.thin_direct_ok(geom(3, 64, 5, 2, 2), 60)
+
+
+def test_batched_entry_points_validate_their_tables_without_a_gpu(lib):
+    """cg_small_ops / cg_scale_slots_h_multi reject over-long or malformed tables before touching the device."""
+    with pytest.raises(L.CslGanCudaError):
+        L.call("cg_small_ops", (L.SmallOp * 33)(), 33, None)
+    with pytest.raises(L.CslGanCudaError):
+        L.call("cg_small_ops", None, 3, None)
+    arr = (L.SmallOp * 1)()
+    arr[0].op, arr[0].n = 99, 5
+    with pytest.raises(L.CslGanCudaError):
+        L.call("cg_small_ops", arr, 1, None)                      # null operands / unknown op
+    with pytest.raises(L.CslGanCudaError):
+        L.call("cg_scale_slots_h_multi", (L.ScaleSeg * 9)(), 9, None)
+    assert L.call("cg_small_ops", arr, 0, None) is None or True   # empty table: nothing to do
+
+
+def test_symmetric_flat_is_unavailable_without_an_nccl_group():
+    """The fused exchange needs an initialised NCCL group with at least two ranks; everything else keeps NCCL / no
+    exchange at all (single process)."""
+    from csl_gan_b200.dist import SymmetricFlat
+    assert SymmetricFlat.available() is False
