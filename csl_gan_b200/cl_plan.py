@@ -217,6 +217,8 @@ class ClLayerPlan:
             if act is None or act.shape[0] != g.shape[0]:
                 raise L.CslGanCudaError(f"{self.name}: backprops of pass {pass_idx} arrived without their activation")
             g = g.contiguous(memory_format=torch.channels_last)       # dense [B][Ho*Wo][M]; a no-op for a channels_last critic
+            if g.data_ptr() % 16:
+                g = g.clone(memory_format=torch.channels_last)        # (a sliced view: the TMA base must be 16-byte aligned)
             # the launch is deferred until the other passes of the step have arrived (or the norms are asked for): both
             # passes in ONE launch waste less of the last round of the 148 persistent CTAs than two launches
             self._pending.append((act, g, slot0, float(scale)))
