@@ -544,6 +544,10 @@ def measure_gc(wl, B, dev, steps, warmup, rank, world, dist_on, want_graph, do_v
     launches0 = L.launch_count
     dp_only()
     out["launches"] = L.launch_count - launches0                                # ABI launch calls per step
+    if dist_on and getattr(eng, "_symm", None) is not None:
+        sy = eng._symm
+        out["allreduce"] = ("fused with the noise: one kernel over NVLink peer-mapped symmetric memory "
+                            f"({'multicast' if sy.use_multicast else 'peer loads / stores'}), two cross-rank barriers")
     timed_fn = dp_only
     dp_graph = None
     if use_graph:
